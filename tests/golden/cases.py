@@ -1,0 +1,58 @@
+"""Seeded case table shared by tests/golden/make_golden.py (which runs the reference) and the tests.
+
+Inputs come from ``numpy.random.RandomState`` (the frozen legacy generator), so they are
+regenerated identically on any box; only reference OUTPUTS are stored as fixtures.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# shape = [Nb, Cin, D, H, W]; roi may contain non-positive entries (fall back to the image dim)
+SW_CASES = {
+    # sw_batch 1 -> centres get the extra leading dim (quirk Q3); clamped last windows on every axis
+    "basic_b1": dict(shape=[1, 1, 40, 36, 44], roi=[16, 16, 16], overlap=0.25, mode="gaussian", sw_batch=1, k=3, seed=1),
+    # anisotropic roi, overlap .5, ragged final batch, W not a multiple of 4
+    "aniso_ragged": dict(shape=[1, 2, 41, 37, 50], roi=[24, 16, 32], overlap=0.5, mode="gaussian", sw_batch=4, k=5, seed=2),
+    # two volumes: predictor batches straddle the volume boundary (quirk Q10)
+    "two_volumes": dict(shape=[2, 1, 30, 28, 33], roi=[16, 16, 16], overlap=0.5, mode="gaussian", sw_batch=3, k=4, seed=3),
+    # one dim smaller than the roi -> symmetric constant pad with the reference's air value (engine/test.py:103-104)
+    "padded_cval": dict(shape=[1, 1, 10, 40, 21], roi=[16, 16, 16], overlap=0.25, mode="gaussian", sw_batch=2, k=3,
+                        seed=4, cval=(0.0 - 0.1943) / 0.2786),
+    "constant_mode": dict(shape=[1, 1, 33, 35, 38], roi=[16, 16, 16], overlap=0.5, mode="constant", sw_batch=4, k=3, seed=5),
+    # BraTS-like: 4 input channels, 3 classes, odd W
+    "brats_like": dict(shape=[1, 4, 36, 36, 31], roi=[16, 16, 16], overlap=0.5, mode="gaussian", sw_batch=4, k=3, seed=6),
+    # roi spans the image on one axis (interval = roi), scalar roi with fall-back (-1) on another
+    "full_axis": dict(shape=[1, 1, 16, 40, 40], roi=[16, -1, 24], overlap=0.25, mode="gaussian", sw_batch=2, k=3, seed=7),
+    "overlap_zero": dict(shape=[1, 1, 32, 40, 48], roi=[16, 16, 16], overlap=0.0, mode="gaussian", sw_batch=5, k=2, seed=8),
+    # high overlap: 3+ windows cover a voxel per axis
+    "overlap_075": dict(shape=[1, 1, 30, 30, 30], roi=[16, 16, 16], overlap=0.75, mode="gaussian", sw_batch=8, k=3, seed=9),
+    # BASELINE.json configs[0] stitching geometry: 128^3, roi 96^3, overlap .25, 14 classes, N=8
+    "cfg1_geometry": dict(shape=[1, 1, 128, 128, 128], roi=[96, 96, 96], overlap=0.25, mode="gaussian", sw_batch=4, k=14, seed=10),
+}
+
+VOTE_CASES = {
+    "k3_m5": dict(shape=[24, 20, 31], k=3, m=5, seed=21),        # BraTS ensemble shape class (cfg4: K=3, M=5)
+    "k14_m5": dict(shape=[17, 23, 29], k=14, m=5, seed=22),
+    "k14_m3_stray": dict(shape=[16, 16, 18], k=14, m=3, seed=23, stray=True),  # labels >= K must be ignored
+    "k2_m1": dict(shape=[8, 9, 10], k=2, m=1, seed=24),          # a single fold can never out-vote background
+    "k16_m15": dict(shape=[12, 12, 13], k=16, m=15, seed=25),
+}
+
+
+def make_volume(case: dict) -> np.ndarray:
+    rs = np.random.RandomState(case["seed"])
+    return rs.standard_normal(case["shape"]).astype(np.float32)
+
+
+def make_vote_maps(case: dict) -> list:
+    """Base map + per-model random relabel (SURVEY.md section 8d synthetic ensemble), uint8."""
+    rs = np.random.RandomState(case["seed"])
+    k, m = case["k"], case["m"]
+    base = rs.randint(0, k, size=case["shape"]).astype(np.uint8)
+    maps = []
+    for _ in range(m):
+        flip = rs.random_sample(case["shape"]) < 0.35
+        hi = k + 3 if case.get("stray") else k
+        noise = rs.randint(0, hi, size=case["shape"]).astype(np.uint8)
+        maps.append(np.where(flip, noise, base).astype(np.uint8))
+    return maps

@@ -1,0 +1,94 @@
+"""Known-answer tests for the MONAI-0.8 helper restatement (oracle/monai08.py).
+
+The reference holds no tests; these answers are hand-derived from the reference call sites
+(engine/utils.py:95-115) and tabulated in SURVEY.md section 8(a-1), 8(a-3) and BASELINE.md section 3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dice as odice
+from oracle import monai08 as M
+from oracle import sliding_window as osw
+
+
+@pytest.mark.parametrize(
+    "image,roi,overlap,interval,starts",
+    [
+        ((128, 128, 128), (96, 96, 96), 0.25, (72, 72, 72), [[0, 32]] * 3),
+        ((512, 512, 200), (96, 96, 96), 0.5, (48, 48, 48),
+         [[0, 48, 96, 144, 192, 240, 288, 336, 384, 416]] * 2 + [[0, 48, 96, 104]]),
+        ((240, 240, 155), (96, 96, 96), 0.5, (48, 48, 48), [[0, 48, 96, 144]] * 2 + [[0, 48, 59]]),
+        ((96, 200, 96), (96, 96, 96), 0.5, (96, 48, 96), [[0], [0, 48, 96, 104], [0]]),
+    ],
+)
+def test_window_grid_known_answers(image, roi, overlap, interval, starts):
+    got_interval, got_starts = osw.window_grid(image, roi, overlap)
+    assert got_interval == interval
+    assert got_starts == starts
+
+
+def test_whole_body_grid():
+    _, starts = osw.window_grid((512, 512, 1024), (96, 96, 96), 0.5)
+    assert [len(s) for s in starts] == [10, 10, 21]
+    assert starts[2][-2:] == [912, 928]
+    assert len(M.dense_patch_slices((512, 512, 1024), (96, 96, 96), (48, 48, 48))) == 2100
+
+
+def test_dense_patch_slices_c_order():
+    sl = M.dense_patch_slices((20, 20, 20), (16, 16, 16), (12, 12, 12))
+    assert len(sl) == 8
+    assert [tuple(s.start for s in w) for w in sl[:3]] == [(0, 0, 0), (0, 0, 4), (0, 4, 0)]
+
+
+def test_fall_back_tuple_and_interval_errors():
+    assert M.fall_back_tuple(96, (128, 100, 90)) == (96, 96, 96)
+    assert M.fall_back_tuple((96, -1, None), (128, 100, 90)) == (96, 100, 90)
+    with pytest.raises(ValueError):
+        M.get_scan_interval((10, 10), (4, 4, 4), 2, 0.5)
+    assert M.get_scan_interval((10, 10, 10), (4, 4, 4), 3, 0.99) == (1, 1, 1)
+
+
+def test_importance_map_96_profile():
+    m = M.compute_importance_map((96, 96, 96), mode="gaussian", sigma_scale=0.125)
+    assert m.dtype == torch.float32 and tuple(m.shape) == (96, 96, 96)
+    assert m[48, 48, 48].item() == 1.0 and m.max().item() == 1.0  # centred at i//2 = 48 (quirk Q2)
+    t = 0.70710678 / 12.0
+
+    def g(x):
+        return 0.5 * (math.erf(t * (x + 0.5)) - math.erf(t * (x - 0.5)))
+
+    prof = m[:, 48, 48].numpy()
+    want = np.array([g(i - 48) / g(0) for i in range(96)])
+    # float32 erf differences cancel badly in the tails (|erf|~1): ~1e-3 relative there, exact at the centre
+    assert np.allclose(prof, want, rtol=3e-3) and np.allclose(prof[24:72], want[24:72], rtol=1e-5)
+    assert prof[0] == pytest.approx(3.37e-4, rel=2e-2) and prof[95] == pytest.approx(4.69e-4, rel=2e-2)
+    assert prof[0] < prof[95]  # asymmetric
+    assert m.min().item() == pytest.approx(prof[0] ** 3, rel=1e-3) and m.min().item() > 0
+    # the map is the rounded outer product ((p_i * p_j) * p_k) / max in float32
+    g32 = M.gaussian_1d(torch.tensor(12.0))[:96]  # taps x=-48..47
+    outer = (g32[:, None, None] * g32[None, :, None]) * g32[None, None, :]
+    assert torch.equal(outer / outer.max(), m)
+
+
+def test_importance_map_constant_and_v12():
+    assert torch.equal(M.compute_importance_map((4, 5, 6), mode="constant"), torch.ones(4, 5, 6))
+    v12 = M.compute_importance_map_v12((96, 96, 96))
+    assert v12.min().item() == pytest.approx(1e-3) and v12.max().item() < 1.0
+
+
+def test_dice_counts_and_nan_rules():
+    pred = np.array([0, 1, 1, 2, 2, 2], dtype=np.uint8)
+    lab = np.array([0, 1, 2, 2, 2, 0], dtype=np.uint8)
+    c = odice.dice_counts(pred, lab, 4)
+    assert c.tolist() == [[1, 1, 2, 0], [1, 2, 3, 0], [2, 1, 3, 0]]
+    d = odice.dice_from_counts(c)
+    assert d[:3].tolist() == [2 / 3, 2 / 3, 4 / 6] and np.isnan(d[3])
+    means, m = odice.class_means(np.stack([d, d]))
+    assert np.isnan(means[3]) and m == pytest.approx(np.nanmean(d))
+    logits = torch.zeros(4, 1, 1, 6)
+    for i, p in enumerate(pred):
+        logits[p, 0, 0, i] = 1.0
+    md = odice.monai_meandice(logits, torch.from_numpy(lab.astype(np.float32)).reshape(1, 1, 1, 6), 4)
+    assert np.allclose(md.numpy()[0, :3], d[:3]) and np.isnan(md.numpy()[0, 3])
