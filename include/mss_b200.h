@@ -1,0 +1,176 @@
+/*
+ * mss_b200.h - C ABI of libmss_b200.so: the B200 (sm_100a) kernels behind the sliding-window
+ * volumetric inference path of zouyunkai/MedicalSemSeg.
+ *
+ * The reference has no native/FFI boundary for this path: it is Python calling Python
+ * (engine/utils.py:19-159 -> MONAI helpers + ATen ops).  This header is therefore the boundary the
+ * new host code binds (medicalsemseg_b200/_lib.py, ctypes); every entry point names the reference
+ * lines whose work it takes over.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*.
+ *   - every device buffer is owned by the caller (PyTorch's caching allocator in practice); the
+ *     library allocates nothing on the device and keeps no global mutable device state.
+ *   - all launches are stream-ordered on `stream`; no entry point synchronises the host.
+ *   - return value: 0 = ok, < 0 = argument error (MSS_E_*), > 0 = a cudaError_t.  A text for the
+ *     last failing call of the calling thread is available from mss_last_error().
+ *   - spatial dims are always ordered (D, H, W) with W the fastest-varying one (NCDHW).
+ */
+#ifndef MSS_B200_H_
+#define MSS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSS_ABI_VERSION 1
+
+#define MSS_OK 0
+#define MSS_E_ARG (-1)         /* null pointer / non-positive size / inconsistent layout            */
+#define MSS_E_UNSUPPORTED (-2) /* valid request the kernels do not implement (e.g. K > MSS_MAX_CLASSES) */
+#define MSS_E_ALIGN (-3)       /* a pointer or pitch violates the documented alignment              */
+#define MSS_E_DRIVER (-4)      /* CUDA driver entry point (tensor-map encode) unavailable            */
+
+#define MSS_MAX_CLASSES 32       /* K for the fused label path; accumulate itself takes any K      */
+#define MSS_MAX_BATCH_PTRS 128   /* predictor batches per mss_accumulate call                      */
+#define MSS_MAX_VOTE_MAPS 15     /* ensemble size M (4-bit vote counters)                          */
+#define MSS_MAX_VOTE_CLASSES 16
+
+/* dtype of the predictor's logits (engine/utils.py:135; fp16/bf16 under autocast, engine/test.py:127) */
+#define MSS_F32 0
+#define MSS_F16 1
+#define MSS_BF16 2
+
+/* importance-map modes (MONAI BlendMode, engine/utils.py:26,113-115) */
+#define MSS_BLEND_CONSTANT 0
+#define MSS_BLEND_PROFILES 1 /* outer product of three caller-supplied 1-D profiles              */
+
+/* 1-D profile variants generated on the device by mss_gaussian_profile */
+#define MSS_GAUSS_MONAI08_ERF 0 /* MONAI 0.8: erf-integrated taps centred at i//2 (oracle/monai08.py) */
+#define MSS_GAUSS_MONAI12_EXP 1 /* MONAI >= 1.2: exp(-x^2/2s^2) on the half-integer grid            */
+
+/* what mss_accumulate does with a voxel once its last covering window has been applied */
+#define MSS_FUSE_NONE 0   /* keep raw weighted sums (multi-GPU slabs: halo exchange comes first)  */
+#define MSS_FUSE_LOGITS 1 /* store sum / count  (engine/utils.py:151)                             */
+#define MSS_FUSE_LABELS 2 /* store only the uint8 argmax label (engine/test.py:140-141)          */
+
+/*
+ * Window layout of one stitched volume (or of one rank's slab of it).
+ *
+ * `image` is the stitched image size after the reference's pad-to-roi (engine/utils.py:97); window
+ * starts per axis come from MONAI dense_patch_slices semantics (engine/utils.py:105-110) and live,
+ * together with per-coordinate cover ranges, in a table built by mss_geom_table_build().  A buffer
+ * handed to the kernels covers the global box [origin, origin + extent) and owns the windows of the
+ * index box [win_lo, win_hi) (single GPU: everything).  Owned windows are enumerated in C order
+ * (D slowest, W fastest) per volume, volumes outermost - the order of engine/utils.py:120-125.
+ */
+typedef struct mss_layout {
+    int32_t image[3];
+    int32_t roi[3];
+    int32_t n_starts[3];
+    int32_t win_lo[3];
+    int32_t win_hi[3];
+    int32_t origin[3];
+    int32_t extent[3];
+    int32_t pitch_w;   /* elements per W-row of accumulator / label / count buffers (>= extent[2])   */
+    int32_t n_volumes; /* Nb                                                                         */
+    int32_t n_classes; /* K                                                                          */
+    const int32_t* table_host; /* table from mss_geom_table_build (host copy, read by the wrappers)  */
+    const int32_t* table_dev;  /* the same table in device memory (read by the kernels)              */
+} mss_layout_t;
+
+/* ---- host-only helpers (no GPU needed) ------------------------------------------------------ */
+
+int mss_abi_version(void);
+const char* mss_last_error(void);
+
+/* Window starts along one axis: MONAI dense_patch_slices per-axis rule (engine/utils.py:108):
+ * n = 1 + min{d >= 0 : d*interval + roi >= image}, start_k = k*interval - max(k*interval+roi-image, 0).
+ * Writes up to `cap` starts, returns the count (or MSS_E_ARG). */
+int mss_axis_starts(int32_t image, int32_t roi, int32_t interval, int32_t* starts_out, int32_t cap);
+
+/* Number of int32 entries of the geometry table for this image / window grid. */
+int64_t mss_geom_table_len(const int32_t image[3], const int32_t n_starts[3]);
+
+/* Build the geometry table (header, per-axis starts, per-coordinate cover ranges) into host memory. */
+int mss_geom_table_build(const int32_t image[3], const int32_t roi[3], const int32_t n_starts[3],
+                         const int32_t* starts_d, const int32_t* starts_h, const int32_t* starts_w,
+                         int32_t* table_out, int64_t table_len);
+
+/* ---- kernels ------------------------------------------------------------------------------- */
+
+/* 1-D gaussian profile of length n on the device (MONAI compute_importance_map's per-axis factor,
+ * engine/utils.py:113-115).  variant: MSS_GAUSS_*.  `profile_out` is device memory, n floats. */
+int mss_gaussian_profile(float* profile_out, int32_t n, float sigma, int32_t variant, void* stream);
+
+/* Importance map [roi_d, roi_h, roi_w] fp32 (engine/utils.py:113-115): ones, or
+ * floor_abs <= 0 (MONAI 0.8): clamp_min(((p_d[i]*p_h[j])*p_w[k]) / max, smallest non-zero entry);
+ * floor_abs > 0 (MONAI >= 1.2): clamp_min((p_d[i]*p_h[j])*p_w[k], max(min entry, floor_abs)).  `profiles` are device
+ * pointers; `scratch` is 8 bytes of device memory. */
+int mss_importance_map(float* map_out, const int32_t roi[3], int32_t mode, const float* prof_d,
+                       const float* prof_h, const float* prof_w, float floor_abs, void* scratch,
+                       void* stream);
+
+/* Patch extraction (engine/utils.py:122-133): gathers owned windows [first_window, first_window +
+ * n_windows) of `lay` into patches_out[n_windows, Cin, roi_d, roi_h, roi_w] fp32 and writes their
+ * relative centres (engine/utils.py:126-130) into centers_out[n_windows, 3].
+ * `volume` is [Nb, Cin, vol_extent] fp32, contiguous; its voxel (0,0,0) sits at stitched-frame
+ * coordinate vol_origin (= the reference's pad offsets, engine/utils.py:98-103); anything outside
+ * reads as `cval`.  Uses TMA 3-D tiled copies when the layout allows (W and roi_w multiples of 4,
+ * 16-byte aligned bases, window inside the volume), plain vector loads otherwise.
+ * use_tma: 1 = auto, 0 = force the non-TMA kernel. */
+int mss_extract_patches(const float* volume, const int32_t vol_origin[3], const int32_t vol_extent[3],
+                        int32_t n_channels, float cval, const mss_layout_t* lay, int64_t first_window,
+                        int32_t n_windows, float* patches_out, float* centers_out, int32_t use_tma,
+                        void* stream);
+
+/* Weighted overlap accumulation (engine/utils.py:137-151), output-stationary and atomics-free.
+ * Applies owned windows [first_window, first_window + n_windows) whose logits live in `n_batches`
+ * predictor outputs (batch_ptrs[i] -> [sw_batch, K, roi] of logits_dtype; the last batch may be
+ * ragged) to the fp32 accumulator acc[Nb, K, extent_d, extent_h, pitch_w]: every covered voxel adds
+ * w*logit per window in ascending window order with separately rounded multiply and add, reads the
+ * accumulator only if an earlier window touched it and writes it once.  `fuse`: MSS_FUSE_*; for
+ * voxels completed by this call MSS_FUSE_LOGITS stores sum/count (count = ascending fp32 sum of the
+ * weights of ALL covering windows of the grid), MSS_FUSE_LABELS stores the first-max argmax into
+ * labels[Nb, extent_d, extent_h, label_pitch_w] and bumps near_ties (uint64, device) for voxels
+ * whose top-2 relative gap is < tie_tol.  acc may be NULL only with MSS_FUSE_LABELS when the call
+ * covers every owned window. */
+int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches,
+                   int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
+                   const float* importance_map, float* acc, int32_t fuse, uint8_t* labels,
+                   int32_t label_pitch_w, float tie_tol, unsigned long long* near_ties, void* stream);
+
+/* Normalise + softmax-argmax -> uint8 (engine/utils.py:151 + engine/test.py:140-141) over the local
+ * box [box_lo, box_hi) of `logits[Nb, K, extent_d, extent_h, pitch_w]`.  normalise != 0 divides by
+ * the window-weight count first (computed on the fly from the table and the importance map);
+ * logits_out (optional, may alias `logits`) receives the normalised values, probs_out (optional)
+ * the softmax probabilities. */
+int mss_finalize_labels(const mss_layout_t* lay, const float* logits, const float* importance_map,
+                        int32_t normalise, const int32_t box_lo[3], const int32_t box_hi[3],
+                        uint8_t* labels, int32_t label_pitch_w, float* logits_out, float* probs_out,
+                        float tie_tol, unsigned long long* near_ties, void* stream);
+
+/* Ensemble majority vote (majority_vote.py:23-37): votes[0] = 1, votes[c>=1] = #{m : map_m == c},
+ * labels >= n_classes ignored, first-max argmax.  maps[i] are device pointers to n_voxels uint8. */
+int mss_majority_vote(const uint8_t* const* maps, int32_t n_maps, int32_t n_classes, int64_t n_voxels,
+                      uint8_t* voted_out, void* stream);
+
+/* Per-class Dice counts (MONAI DiceMetric inputs, engine/test.py:50-56): counts[0][c] = #(pred==c &
+ * label==c), counts[1][c] = #(pred==c), counts[2][c] = #(label==c) as int64[3][n_classes], ADDED to
+ * the existing contents of `counts` (device).  label_dtype: 0 = uint8, 1 = float32 (integer valued,
+ * as the reference's loaders provide).  Values outside [0, n_classes) are counted nowhere. */
+int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
+                    int32_t n_classes, long long* counts, void* stream);
+
+/* Halo reduction for z-slab partitioning: dst[i] += src[i] over a [n_rows, row_len] fp32 block with
+ * independent row pitches (the receiving rank adds its neighbour's partial sums). */
+int mss_halo_add(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t n_rows,
+                 int64_t row_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSS_B200_H_ */

@@ -1,0 +1,210 @@
+// Normalise + softmax + argmax -> uint8 label map
+// (replaces `output_image / count_map` of engine/utils.py:151 and the softmax -> D2H -> np.argmax -> uint8
+// of engine/test.py:140-141 / :81-82; the eval variant AsDiscrete(argmax=True) of engine/test.py:29).
+//
+// One thread owns 4 consecutive W voxels and streams the K class planes once (16-byte loads).  The
+// K-channel-replicated count_map of the reference (engine/utils.py:142,148) is never materialised:
+// the weight count of a voxel is re-derived from the geometry table and the (L2-resident) importance
+// map as the ascending fp32 sum over its covering windows - the same additions in the same order.
+#include "common.cuh"
+#include "labels.cuh"
+
+namespace mss {
+
+constexpr int kFinThreads = 256;
+
+struct FinParams {
+    Geo g;
+    const float* logits;
+    const float* imp;
+    int normalise;
+    int box_lo[3];
+    int box_n[3];
+    int nq;
+    uint8_t* labels;
+    int label_pitch;
+    float* logits_out;
+    float* probs_out;
+    float tie_tol;
+    unsigned long long* near_ties;
+};
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinParams p) {
+    const Geo& g = p.g;
+    const int t = blockIdx.x * kFinThreads + threadIdx.x;
+    if (t >= p.nq * p.box_n[1]) return;
+    const int ld = p.box_lo[0] + blockIdx.y;
+    const int lh = p.box_lo[1] + t / p.nq;
+    const int lw = p.box_lo[2] + (t % p.nq) * 4;
+    const int b = blockIdx.z;
+    const int box_hi_w = p.box_lo[2] + p.box_n[2];
+    bool valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) valid[e] = lw + e < box_hi_w && lw + e < g.ext[2];
+    if (!valid[0]) return;
+
+    float cnt[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p.normalise) {
+        const int gd = ld + g.org[0], gh = lh + g.org[1], gw = lw + g.org[2];
+        const int rh = g.roi[1], rw = g.roi[2];
+        const int cvd = g.cover[0][gd], cvh = g.cover[1][gh];
+        int wlo = 0x7fffffff, whi = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (valid[e]) {
+                const int c = g.cover[2][gw + e];
+                wlo = min(wlo, c & 0xffff);
+                whi = max(whi, c >> 16);
+            }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cnt[e] = 0.f;
+        for (int id = cvd & 0xffff; id < (cvd >> 16); ++id)
+            for (int ih = cvh & 0xffff; ih < (cvh >> 16); ++ih) {
+                const float* row = p.imp + (static_cast<long long>(gd - g.starts[0][id]) * rh + (gh - g.starts[1][ih])) * rw;
+                for (int iw = wlo; iw < whi; ++iw) {
+                    const int ww = gw - g.starts[2][iw];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (valid[e] && ww + e >= 0 && ww + e < rw) cnt[e] = __fadd_rn(cnt[e], __ldg(row + ww + e));
+                }
+            }
+    }
+
+    const long long plane = static_cast<long long>(g.ext[1]) * g.pitch;
+    const long long cstride = static_cast<long long>(g.ext[0]) * plane;
+    const long long vox = static_cast<long long>(b) * g.K * cstride + static_cast<long long>(ld) * plane +
+                          static_cast<long long>(lh) * g.pitch + lw;
+    const float* src = p.logits + vox;
+
+    ArgmaxState am[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) am[e].reset();
+    const bool full = valid[3];
+    constexpr int U = 8;
+    for (int k0 = 0; k0 < g.K; k0 += U) {
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (k0 + k < g.K) v[k] = *reinterpret_cast<const float4*>(src + (k0 + k) * cstride);
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (k0 + k < g.K) {
+                if (p.normalise) {
+                    v[k].x = __fdiv_rn(v[k].x, cnt[0]);
+                    v[k].y = __fdiv_rn(v[k].y, cnt[1]);
+                    v[k].z = __fdiv_rn(v[k].z, cnt[2]);
+                    v[k].w = __fdiv_rn(v[k].w, cnt[3]);
+                }
+                am[0].push(v[k].x, k0 + k);
+                am[1].push(v[k].y, k0 + k);
+                am[2].push(v[k].z, k0 + k);
+                am[3].push(v[k].w, k0 + k);
+                if (p.logits_out != nullptr) {
+                    float* dst = p.logits_out + vox + (k0 + k) * cstride;
+                    if (full) {
+                        *reinterpret_cast<float4*>(dst) = v[k];
+                    } else {
+                        dst[0] = v[k].x;
+                        if (valid[1]) dst[1] = v[k].y;
+                        if (valid[2]) dst[2] = v[k].z;
+                    }
+                }
+            }
+    }
+
+    if (p.probs_out != nullptr) {
+        // softmax(dim=classes) = exp(x - max) / sum exp(x - max), second and third sweep over the planes
+        const float* nsrc = (p.logits_out != nullptr) ? p.logits_out + vox : src;
+        const bool renorm = p.normalise && p.logits_out == nullptr;
+        float m[4] = {am[0].best, am[1].best, am[2].best, am[3].best};
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < g.K; ++k) {
+            float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
+            float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
+                s[e] += expf(xv[e] - m[e]);
+            }
+        }
+        for (int k = 0; k < g.K; ++k) {
+            float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
+            float xv[4] = {x.x, x.y, x.z, x.w};
+            float* dst = p.probs_out + vox + k * cstride;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
+                if (valid[e]) dst[e] = expf(xv[e] - m[e]) / s[e];
+            }
+        }
+    }
+
+    if (p.labels != nullptr) {
+        uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
+                       static_cast<long long>(lh) * p.label_pitch + lw;
+        unsigned packed = 0, ties = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (valid[e]) {
+                packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
+                ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
+            }
+        if (full && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
+            *reinterpret_cast<unsigned*>(lab) = packed;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (valid[e]) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+        }
+        if (ties && p.near_ties != nullptr) atomicAdd(p.near_ties, static_cast<unsigned long long>(ties));
+    }
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" int mss_finalize_labels(const mss_layout_t* lay, const float* logits, const float* importance_map,
+                                   int32_t normalise, const int32_t box_lo[3], const int32_t box_hi[3], uint8_t* labels,
+                                   int32_t label_pitch_w, float* logits_out, float* probs_out, float tie_tol,
+                                   unsigned long long* near_ties, void* stream) {
+    FinParams p;
+    int rc = make_geo(lay, &p.g);
+    if (rc != MSS_OK) return rc;
+    const Geo& g = p.g;
+    MSS_REQUIRE(logits != nullptr && box_lo != nullptr && box_hi != nullptr, MSS_E_ARG, "finalize_labels: null argument");
+    MSS_REQUIRE(labels != nullptr || logits_out != nullptr || probs_out != nullptr, MSS_E_ARG,
+                "finalize_labels: nothing to write");
+    MSS_REQUIRE(!normalise || importance_map != nullptr, MSS_E_ARG, "finalize_labels: normalise needs the importance map");
+    MSS_REQUIRE(g.pitch % 4 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0, MSS_E_ALIGN,
+                "finalize_labels: logits need a pitch multiple of 4 and a 16-byte aligned base");
+    MSS_REQUIRE((logits_out == nullptr || reinterpret_cast<uintptr_t>(logits_out) % 16 == 0) &&
+                    (probs_out == nullptr || reinterpret_cast<uintptr_t>(probs_out) % 16 == 0),
+                MSS_E_ALIGN, "finalize_labels: outputs must be 16-byte aligned");
+    MSS_REQUIRE(labels == nullptr || (g.K <= 255 && label_pitch_w >= g.ext[2]), MSS_E_ARG,
+                "finalize_labels: uint8 labels need K <= 255 and label_pitch_w >= extent W");
+    for (int a = 0; a < 3; ++a) {
+        MSS_REQUIRE(0 <= box_lo[a] && box_lo[a] < box_hi[a] && box_hi[a] <= g.ext[a], MSS_E_ARG,
+                    "finalize_labels: axis %d box [%d,%d) outside the buffer (%d)", a, box_lo[a], box_hi[a], g.ext[a]);
+        p.box_lo[a] = box_lo[a];
+        p.box_n[a] = box_hi[a] - box_lo[a];
+    }
+    MSS_REQUIRE(box_lo[2] % 4 == 0, MSS_E_ALIGN, "finalize_labels: box_lo W (%d) must be a multiple of 4", box_lo[2]);
+    p.nq = (p.box_n[2] + 3) / 4;
+    p.logits = logits;
+    p.imp = importance_map;
+    p.normalise = normalise;
+    p.labels = labels;
+    p.label_pitch = label_pitch_w;
+    p.logits_out = logits_out;
+    p.probs_out = probs_out;
+    p.tie_tol = tie_tol;
+    p.near_ties = near_ties;
+    const long long per_plane = static_cast<long long>(p.nq) * p.box_n[1];
+    dim3 grid(static_cast<unsigned>((per_plane + kFinThreads - 1) / kFinThreads), static_cast<unsigned>(p.box_n[0]),
+              static_cast<unsigned>(g.nb));
+    MSS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MSS_E_UNSUPPORTED, "finalize_labels: box too large for one launch");
+    finalize_kernel<<<grid, kFinThreads, 0, as_stream(stream)>>>(p);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}

@@ -1,0 +1,489 @@
+"""Sliding-window volumetric inference on B200: the drop-in for engine/utils.py::sliding_window_inference.
+
+Public surface (mirrors what engine/test.py, engine/val.py, run_test.py and run_evaluation.py call):
+
+* ``sliding_window_inference(inputs, affine, roi_size, sw_batch_size, predictor, overlap, mode, ...)``
+  - same signature and return value as engine/utils.py:19-34 (stitched fp32 logits ``[Nb, K, D, H, W]``).
+* ``SlidingWindowInferer(roi_size, sw_batch_size, overlap, mode, ..., cval)`` - callable as
+  ``inferer(inputs=..., network=...)`` like the MONAI object built at run_evaluation.py:68-74.
+* ``sliding_window_infer(volume, model, roi, overlap, mode='gaussian')`` - the fused path: uint8 label
+  map straight from the accumulation kernel (engine/utils.py:19-159 + engine/test.py:140-141 in one go).
+
+Only the backbone forward is PyTorch (the caller's module, called once per patch batch on the current
+stream under the caller's no_grad/autocast context); extraction, weighting, accumulation, normalisation
+and argmax are the CUDA kernels of libmss_b200.so.  There is no CPU or ATen fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .grid import PAD_MODES, WindowGrid, _option, make_grid
+from .importance import importance_map as build_importance_map
+
+_DTYPES = {torch.float32: _lib.MSS_F32, torch.float16: _lib.MSS_F16, torch.bfloat16: _lib.MSS_BF16}
+
+
+@dataclass
+class InferStats:
+    """What one stitched volume cost; filled when ``stats=`` is passed."""
+
+    n_windows: int = 0
+    n_predictor_calls: int = 0
+    n_accumulate_calls: int = 0
+    gpu_launches: int = 0                      # kernels of libmss_b200.so launched
+    extract_bytes: int = 0                     # algorithmic bytes, SURVEY.md section 8(d)
+    accumulate_bytes: int = 0
+    used_tma: bool = False
+    accumulator_allocated: bool = False
+    _near_ties: Optional[torch.Tensor] = field(default=None, repr=False)
+    events: Dict[str, List[Tuple[Any, Any]]] = field(default_factory=dict, repr=False)
+
+    @property
+    def near_ties(self) -> int:
+        """Voxels whose top-2 relative logit gap is below ``tie_tol`` (synchronises)."""
+        return 0 if self._near_ties is None else int(self._near_ties.item())
+
+    def kernel_ms(self) -> Dict[str, float]:
+        """Summed CUDA-event time per kernel family (needs ``time_kernels=True``; synchronises)."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.events.items()}
+
+    def kernel_launch_ms(self, name: str) -> List[float]:
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in self.events.get(name, [])]
+
+
+class _Timer:
+    def __init__(self, stats: Optional[InferStats], enabled: bool):
+        self.stats, self.enabled = stats, enabled and stats is not None
+
+    def __call__(self, name: str):
+        return _Span(self, name)
+
+
+class _Span:
+    def __init__(self, t: _Timer, name: str):
+        self.t, self.name = t, name
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.t.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.stats.events.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
+class StitchPlan:
+    """Geometry of one (volume shape, roi, overlap) on one device: window grid + device copy of its table."""
+
+    def __init__(self, grid: WindowGrid, device: torch.device, n_volumes: int,
+                 win_lo: Sequence[int] = (0, 0, 0), win_hi: Optional[Sequence[int]] = None,
+                 origin: Sequence[int] = (0, 0, 0), extent: Optional[Sequence[int]] = None):
+        self.grid = grid
+        self.device = device
+        self.n_volumes = n_volumes
+        self.table_host = np.ascontiguousarray(grid.table, dtype=np.int32)
+        self.table_dev = torch.from_numpy(self.table_host).to(device)
+        self.win_lo = tuple(win_lo)
+        self.win_hi = tuple(win_hi) if win_hi is not None else grid.n_starts
+        self.origin = tuple(origin)
+        self.extent = tuple(extent) if extent is not None else grid.image_size
+        self.pitch_w = (self.extent[2] + 3) // 4 * 4
+        nl = [h - l for l, h in zip(self.win_lo, self.win_hi)]
+        self.n_local = nl[0] * nl[1] * nl[2]
+
+    def layout(self, n_classes: int) -> _lib.Layout:
+        g = self.grid
+        lay = _lib.Layout()
+        lay.image = _lib.I3(*g.image_size)
+        lay.roi = _lib.I3(*g.roi)
+        lay.n_starts = _lib.I3(*g.n_starts)
+        lay.win_lo = _lib.I3(*self.win_lo)
+        lay.win_hi = _lib.I3(*self.win_hi)
+        lay.origin = _lib.I3(*self.origin)
+        lay.extent = _lib.I3(*self.extent)
+        lay.pitch_w = self.pitch_w
+        lay.n_volumes = self.n_volumes
+        lay.n_classes = max(int(n_classes), 1)
+        lay.table_host = self.table_host.ctypes.data
+        lay.table_dev = self.table_dev.data_ptr()
+        return lay
+
+
+_PLAN_CACHE: Dict[Any, StitchPlan] = {}
+
+
+def get_plan(spatial: Sequence[int], roi_size: Any, overlap: float, device: torch.device, n_volumes: int) -> StitchPlan:
+    roi_key = tuple(roi_size) if isinstance(roi_size, (list, tuple)) else roi_size
+    key = (tuple(spatial), roi_key, float(overlap), str(device), n_volumes)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = StitchPlan(make_grid(spatial, roi_size, overlap), device, n_volumes)
+        if len(_PLAN_CACHE) > 64:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def _default_group_bytes(device: torch.device) -> int:
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(min(24 << 30, free // 2))
+
+
+class Stitcher:
+    """Drives libmss_b200.so for one stitched volume batch: extract -> predictor -> deferred accumulate.
+
+    Predictor outputs are kept alive (HBM is large: 180 GB) and applied in groups by one output-stationary
+    kernel launch per group, so an accumulator voxel is read and written at most once per group - or
+    never, when a single group holds every window and the fused kernel writes labels directly.
+    """
+
+    def __init__(self, plan: StitchPlan, imp: torch.Tensor, *, fuse: int, sw_batch: int, tie_tol: float = 1e-5,
+                 group_bytes: Optional[int] = None, stats: Optional[InferStats] = None, time_kernels: bool = False,
+                 use_tma: bool = True):
+        self.lib = _lib.load()
+        self.plan, self.imp, self.fuse, self.sw_batch = plan, imp, fuse, int(sw_batch)
+        self.tie_tol = float(tie_tol)
+        self.group_bytes = group_bytes
+        self.stats = stats
+        self.timer = _Timer(stats, time_kernels)
+        self.use_tma = use_tma
+        self.device = plan.device
+        self.total = plan.n_local * plan.n_volumes
+        self.pending: List[torch.Tensor] = []
+        self.pending_first = 0
+        self.pending_windows = 0
+        self.acc: Optional[torch.Tensor] = None
+        self.labels: Optional[torch.Tensor] = None
+        self.near = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.K: Optional[int] = None
+        self.lay: Optional[_lib.Layout] = None
+        self.group_batches = 1
+        self.logits_dtype: Optional[torch.dtype] = None
+
+    # -- extraction -----------------------------------------------------------------------------
+    def extract(self, volume: torch.Tensor, first: int, n: int, cval: float,
+                vol_origin: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        g = self.plan.grid
+        cin = volume.shape[1]
+        patches = torch.empty((n, cin) + tuple(g.roi), dtype=torch.float32, device=self.device)
+        centers = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        lay = self.lay if self.lay is not None else self.plan.layout(1)
+        vorg = _lib.I3(*(vol_origin if vol_origin is not None else g.pad_lo))
+        vext = _lib.I3(*volume.shape[2:])
+        stream = torch.cuda.current_stream().cuda_stream
+        with self.timer("extract"):
+            rc = self.lib.mss_extract_patches(volume.data_ptr(), vorg, vext, cin, float(cval), C.byref(lay), first, n,
+                                              patches.data_ptr(), centers.data_ptr(), 1 if self.use_tma else 0, stream)
+        _lib.check(rc, "mss_extract_patches")
+        if self.stats is not None:
+            self.stats.gpu_launches += 1
+            self.stats.extract_bytes += 8 * n * cin * g.roi[0] * g.roi[1] * g.roi[2]
+        return patches, centers
+
+    # -- accumulation ---------------------------------------------------------------------------
+    def _first_batch(self, logits: torch.Tensor) -> None:
+        g = self.plan.grid
+        self.K = int(logits.shape[1])
+        self.lay = self.plan.layout(self.K)
+        self.logits_dtype = logits.dtype if logits.dtype in _DTYPES else torch.float32
+        esz = 4 if self.logits_dtype == torch.float32 else 2
+        per_batch = self.sw_batch * self.K * g.roi[0] * g.roi[1] * g.roi[2] * esz
+        budget = self.group_bytes if self.group_bytes is not None else _default_group_bytes(self.device)
+        self.group_batches = int(max(1, min(_lib.MAX_BATCH_PTRS, budget // max(per_batch, 1))))
+        n_batches_total = -(-self.total // self.sw_batch)
+        single_group = n_batches_total <= self.group_batches
+        ext = self.plan.extent
+        if self.fuse == _lib.FUSE_LABELS:
+            self.labels = torch.empty((self.plan.n_volumes,) + tuple(ext), dtype=torch.uint8, device=self.device)
+        if not (self.fuse == _lib.FUSE_LABELS and single_group):
+            # no memset: the kernel reads an accumulator element only after an earlier launch wrote it
+            self.acc = torch.empty((self.plan.n_volumes, self.K, ext[0], ext[1], self.plan.pitch_w), dtype=torch.float32,
+                                   device=self.device)
+            if self.stats is not None:
+                self.stats.accumulator_allocated = True
+
+    def push(self, logits: torch.Tensor, n: int) -> None:
+        """Hand over the predictor output of the next ``n`` windows (engine/utils.py:135-148)."""
+        g = self.plan.grid
+        if self.K is None:
+            if logits.dim() != 5:
+                raise ValueError(f"predictor must return [B, K, D, H, W] logits, got shape {tuple(logits.shape)}")
+            self._first_batch(logits)
+        if tuple(logits.shape) != (n, self.K) + tuple(g.roi):
+            raise ValueError(f"predictor returned {tuple(logits.shape)}, expected {(n, self.K) + tuple(g.roi)}")
+        if logits.dtype != self.logits_dtype:
+            logits = logits.to(self.logits_dtype)
+        if not logits.is_contiguous():
+            logits = logits.contiguous()
+        if any(logits.data_ptr() == t.data_ptr() for t in self.pending):
+            logits = logits.clone()  # a predictor that reuses its output buffer (e.g. a captured CUDA graph)
+        self.pending.append(logits)
+        self.pending_windows += n
+        if len(self.pending) >= self.group_batches or self.pending_first + self.pending_windows >= self.total:
+            self.flush()
+
+    def flush(self) -> None:
+        if not self.pending:
+            return
+        g = self.plan.grid
+        ptrs = (C.c_void_p * len(self.pending))(*[t.data_ptr() for t in self.pending])
+        stream = torch.cuda.current_stream().cuda_stream
+        with self.timer("accumulate"):
+            rc = self.lib.mss_accumulate(
+                C.byref(self.lay), ptrs, len(self.pending), self.sw_batch, _DTYPES[self.logits_dtype], self.pending_first,
+                self.pending_windows, self.imp.data_ptr(), None if self.acc is None else self.acc.data_ptr(), self.fuse,
+                None if self.labels is None else self.labels.data_ptr(), self.plan.extent[2], self.tie_tol,
+                self.near.data_ptr(), stream)
+        _lib.check(rc, "mss_accumulate")
+        if self.stats is not None:
+            self.stats.gpu_launches += 1
+            self.stats.n_accumulate_calls += 1
+            self.stats.accumulate_bytes += 12 * self.pending_windows * self.K * g.roi[0] * g.roi[1] * g.roi[2]
+        self.pending_first += self.pending_windows
+        self.pending_windows = 0
+        self.pending = []  # the kernel is stream-ordered before the allocator can hand these blocks out again
+
+
+def _as_cuda_volume(inputs: torch.Tensor, device: Any) -> torch.Tensor:
+    if not torch.cuda.is_available():
+        raise _lib.MssError("medicalsemseg_b200 needs a CUDA device (B200); there is no CPU fallback")
+    if inputs.dim() != 5:
+        raise ValueError("inputs must be [N, C, D, H, W] (3-D volumes, channel-first, with a batch dim)")
+    dev = torch.device(device) if device is not None else inputs.device
+    if dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    vol = inputs.to(device=dev, dtype=torch.float32, non_blocking=True)  # the H2D of engine/test.py:116
+    return vol.contiguous()
+
+
+def _run(inputs: torch.Tensor, predictor: Callable[..., torch.Tensor], roi_size: Any, sw_batch_size: int, overlap: float,
+         mode: Any, sigma_scale: Any, padding_mode: Any, cval: float, affine: Optional[torch.Tensor], tuple_input: bool,
+         fuse: int, device: Any, args: Sequence[Any], kwargs: Dict[str, Any], *, tie_tol: float = 1e-5,
+         importance_map: Optional[torch.Tensor] = None, group_bytes: Optional[int] = None,
+         stats: Optional[InferStats] = None, time_kernels: bool = False, imp_variant: str = "monai08",
+         imp_taps: str = "host", use_tma: bool = True) -> Stitcher:
+    if overlap < 0 or overlap >= 1:
+        raise AssertionError("overlap must be >= 0 and < 1.")  # engine/utils.py:82-83
+    pad_mode = _option(padding_mode, PAD_MODES, "padding_mode")
+    vol = _as_cuda_volume(inputs, device)
+    dev = vol.device
+    with torch.cuda.device(dev):
+        nb = vol.shape[0]
+        spatial = tuple(vol.shape[2:])
+        plan = get_plan(spatial, roi_size, overlap, dev, nb)
+        g = plan.grid
+        if g.padded and pad_mode != "constant":
+            # non-constant padding only ever applies to volumes smaller than one window: pad on the device
+            # with the same F.pad call as engine/utils.py:103 and stitch the padded volume unpadded
+            pads: List[int] = []
+            for a in (2, 1, 0):
+                diff = g.image_size[a] - g.orig_size[a]
+                pads.extend([diff // 2, diff - diff // 2])
+            vol = F.pad(vol, pad=pads, mode=pad_mode).contiguous()
+            vol_origin: Tuple[int, int, int] = (0, 0, 0)
+        else:
+            vol_origin = g.pad_lo
+        if importance_map is None:
+            imp = build_importance_map(g.roi, mode, sigma_scale, dev, variant=imp_variant, taps=imp_taps)
+        else:
+            imp = importance_map.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(imp.shape) != tuple(g.roi):
+                raise ValueError(f"importance_map must have the roi shape {g.roi}, got {tuple(imp.shape)}")
+        st = Stitcher(plan, imp, fuse=fuse, sw_batch=sw_batch_size, tie_tol=tie_tol, group_bytes=group_bytes, stats=stats,
+                      time_kernels=time_kernels, use_tma=use_tma)
+        if stats is not None:
+            stats.n_windows = st.total
+            stats._near_ties = st.near
+        if affine is not None and isinstance(affine, torch.Tensor):
+            affine = affine.to(dev)
+        for first in range(0, st.total, sw_batch_size):  # engine/utils.py:120
+            n = min(sw_batch_size, st.total - first)
+            patches, centers = st.extract(vol, first, n, cval, vol_origin)
+            if sw_batch_size == 1:
+                centers = centers.unsqueeze(0)  # engine/utils.py:131-132 (quirk Q3)
+            model_in = (patches, centers, affine) if tuple_input else patches  # engine/utils.py:134
+            with st.timer("predictor"):
+                logits = predictor(model_in, *args, **kwargs)  # engine/utils.py:135
+            if logits.device != dev:
+                logits = logits.to(dev)
+            st.push(logits, n)
+            if stats is not None:
+                stats.n_predictor_calls += 1
+        st.flush()
+    return st
+
+
+def _crop(t: torch.Tensor, g: WindowGrid) -> torch.Tensor:
+    """Undo the pad-to-roi (engine/utils.py:153-159) and the internal W pitch: a view, like the reference returns."""
+    sl = tuple(slice(g.pad_lo[a], g.pad_lo[a] + g.orig_size[a]) for a in range(3))
+    return t[(Ellipsis,) + sl]
+
+
+def sliding_window_inference(
+    inputs: torch.Tensor,
+    affine: Optional[torch.Tensor],
+    roi_size: Union[Sequence[int], int],
+    sw_batch_size: int,
+    predictor: Callable[..., torch.Tensor],
+    overlap: float = 0.25,
+    mode: Any = "constant",
+    sigma_scale: Union[Sequence[float], float] = 0.125,
+    padding_mode: Any = "constant",
+    cval: float = 0.0,
+    sw_device: Union[torch.device, str, None] = None,
+    device: Union[torch.device, str, None] = None,
+    *args: Any,
+    **kwargs: Any,
+) -> torch.Tensor:
+    """Drop-in for ``engine/utils.py::sliding_window_inference`` (:19-159), same arguments, same result.
+
+    The predictor receives the reference's 3-tuple ``(patches, centers, affine)`` (:134).  ``device`` /
+    ``sw_device`` must name the same CUDA device (stitching on the CPU is not provided).  Keyword-only
+    extras understood and NOT forwarded to the predictor: ``mss_stats``, ``mss_importance_map``,
+    ``mss_group_bytes``, ``mss_tuple_input``, ``mss_time_kernels``, ``mss_imp_variant``, ``mss_imp_taps``.
+    """
+    opts = {k: kwargs.pop(k) for k in list(kwargs) if k.startswith("mss_")}
+    for d in (device, sw_device):
+        if d is not None and torch.device(d).type != "cuda":
+            raise _lib.MssError("medicalsemseg_b200 stitches on the GPU only: device/sw_device must be CUDA devices")
+    st = _run(inputs, predictor, roi_size, sw_batch_size, overlap, mode, sigma_scale, padding_mode, cval, affine,
+              opts.get("mss_tuple_input", True), _lib.FUSE_LOGITS, device, args, kwargs,
+              importance_map=opts.get("mss_importance_map"), group_bytes=opts.get("mss_group_bytes"),
+              stats=opts.get("mss_stats"), time_kernels=opts.get("mss_time_kernels", False),
+              imp_variant=opts.get("mss_imp_variant", "monai08"), imp_taps=opts.get("mss_imp_taps", "host"))
+    return _crop(st.acc, st.plan.grid)
+
+
+class SlidingWindowInferer:
+    """Stand-in for ``monai.inferers.SlidingWindowInferer`` as built at run_evaluation.py:68-74 and called at
+    engine/test.py:47 (``inferer(inputs=..., network=...)``): the network gets the PLAIN patch tensor (quirk Q6)."""
+
+    def __init__(self, roi_size: Union[Sequence[int], int], sw_batch_size: int = 1, overlap: float = 0.25,
+                 mode: Any = "constant", sigma_scale: Union[Sequence[float], float] = 0.125,
+                 padding_mode: Any = "constant", cval: float = 0.0, sw_device: Any = None, device: Any = None) -> None:
+        self.roi_size, self.sw_batch_size, self.overlap = roi_size, sw_batch_size, overlap
+        self.mode, self.sigma_scale, self.padding_mode, self.cval = mode, sigma_scale, padding_mode, cval
+        self.sw_device, self.device = sw_device, device
+
+    def __call__(self, inputs: torch.Tensor, network: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
+        kwargs.setdefault("mss_tuple_input", False)
+        return sliding_window_inference(inputs, None, self.roi_size, self.sw_batch_size, network, self.overlap, self.mode,
+                                        self.sigma_scale, self.padding_mode, self.cval, self.sw_device, self.device,
+                                        *args, **kwargs)
+
+
+def sliding_window_infer(
+    volume: torch.Tensor,
+    model: Callable[..., torch.Tensor],
+    roi: Union[Sequence[int], int] = 96,
+    overlap: float = 0.5,
+    mode: Any = "gaussian",
+    *,
+    sw_batch_size: int = 4,
+    sigma_scale: Union[Sequence[float], float] = 0.125,
+    padding_mode: Any = "constant",
+    cval: float = 0.0,
+    affine: Optional[torch.Tensor] = None,
+    tuple_input: Optional[bool] = None,
+    return_logits: bool = False,
+    tie_tol: float = 1e-5,
+    device: Any = None,
+    stats: Optional[InferStats] = None,
+    importance_map: Optional[torch.Tensor] = None,
+    group_bytes: Optional[int] = None,
+    time_kernels: bool = False,
+    imp_variant: str = "monai08",
+    imp_taps: str = "host",
+    use_tma: bool = True,
+) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """Sliding-window inference straight to the uint8 label map ``[Nb, D, H, W]``.
+
+    Equivalent to ``sliding_window_inference`` (engine/utils.py:19-159) followed by
+    ``softmax -> argmax -> uint8`` (engine/test.py:140-141; take ``[0]`` for the reference's single volume),
+    but the stitched logits never exist in memory unless ``return_logits=True``: the accumulation kernel
+    finishes each voxel as soon as its last window arrives.  ``tuple_input=None`` hands the model the
+    reference's ``(patches, centers, affine)`` tuple when ``affine`` is given and the plain patch tensor
+    otherwise.  Voxels whose top-2 logit gap is below ``tie_tol`` are counted in ``stats.near_ties``.
+    """
+    if tuple_input is None:
+        tuple_input = affine is not None
+    if return_logits:
+        st = _run(volume, model, roi, sw_batch_size, overlap, mode, sigma_scale, padding_mode, cval, affine, tuple_input,
+                  _lib.FUSE_LOGITS, device, (), {}, tie_tol=tie_tol, importance_map=importance_map,
+                  group_bytes=group_bytes, stats=stats, time_kernels=time_kernels, imp_variant=imp_variant,
+                  imp_taps=imp_taps, use_tma=use_tma)
+        labels = labels_from_logits(st.acc, st, tie_tol=tie_tol, normalise=False)
+        return _crop(labels, st.plan.grid), _crop(st.acc, st.plan.grid)
+    st = _run(volume, model, roi, sw_batch_size, overlap, mode, sigma_scale, padding_mode, cval, affine, tuple_input,
+              _lib.FUSE_LABELS, device, (), {}, tie_tol=tie_tol, importance_map=importance_map, group_bytes=group_bytes,
+              stats=stats, time_kernels=time_kernels, imp_variant=imp_variant, imp_taps=imp_taps, use_tma=use_tma)
+    return _crop(st.labels, st.plan.grid)
+
+
+def labels_from_logits(acc: torch.Tensor, st: Stitcher, *, tie_tol: float = 1e-5, normalise: bool = False,
+                       box: Optional[Tuple[Sequence[int], Sequence[int]]] = None,
+                       labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mss_finalize_labels`` on a stitcher's accumulator: [normalise +] argmax -> uint8 (engine/test.py:140-141)."""
+    plan = st.plan
+    ext = plan.extent
+    if labels is None:
+        labels = torch.empty((plan.n_volumes,) + tuple(ext), dtype=torch.uint8, device=acc.device)
+    lo, hi = box if box is not None else ((0, 0, 0), ext)
+    stream = torch.cuda.current_stream().cuda_stream
+    with st.timer("finalize"):
+        rc = st.lib.mss_finalize_labels(C.byref(st.lay), acc.data_ptr(), st.imp.data_ptr(), 1 if normalise else 0,
+                                        _lib.I3(*lo), _lib.I3(*hi), labels.data_ptr(), ext[2], None, None, float(tie_tol),
+                                        st.near.data_ptr(), stream)
+    _lib.check(rc, "mss_finalize_labels")
+    if st.stats is not None:
+        st.stats.gpu_launches += 1
+    return labels
+
+
+def logits_to_labels(logits: torch.Tensor, *, tie_tol: float = 1e-5, return_probs: bool = False,
+                     stats: Optional[InferStats] = None):
+    """Stand-alone ``softmax(outputs, 1) -> argmax -> uint8`` of engine/test.py:140-141 / :81-82 for stitched logits
+    ``[Nb, K, D, H, W]`` that already live on the GPU: returns uint8 ``[Nb, D, H, W]`` (and the probabilities)."""
+    if logits.dim() != 5 or not logits.is_cuda:
+        raise ValueError("logits must be a CUDA tensor [N, K, D, H, W]")
+    lib = _lib.load()
+    nb, k, d, h, w = logits.shape
+    src = logits.to(torch.float32)
+    wp = (w + 3) // 4 * 4
+    if wp != w or not src.is_contiguous() or src.data_ptr() % 16:
+        buf = torch.empty((nb, k, d, h, wp), dtype=torch.float32, device=logits.device)
+        buf[..., :w] = src
+        src = buf
+    with torch.cuda.device(logits.device):
+        grid = make_grid((d, h, w), (d, h, w), 0.0)
+        plan = StitchPlan(grid, logits.device, nb)
+        lay = plan.layout(k)
+        labels = torch.empty((nb, d, h, w), dtype=torch.uint8, device=logits.device)
+        probs = torch.empty_like(src) if return_probs else None
+        near = torch.zeros(1, dtype=torch.int64, device=logits.device)
+        rc = lib.mss_finalize_labels(C.byref(lay), src.data_ptr(), None, 0, _lib.I3(0, 0, 0), _lib.I3(d, h, w),
+                                     labels.data_ptr(), w, None, None if probs is None else probs.data_ptr(),
+                                     float(tie_tol), near.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_finalize_labels")
+    if stats is not None:
+        stats._near_ties = near
+        stats.gpu_launches += 1
+    if return_probs:
+        return labels, probs[..., :w]
+    return labels

@@ -1,0 +1,78 @@
+"""Per-class Dice from exact confusion counts: what engine/test.py:28-31,50-69 gets out of MONAI's
+AsDiscrete + DiceMetric(include_background=True, reduction="none", get_not_nans=True)."""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def dice_counts(pred: torch.Tensor, label: torch.Tensor, n_classes: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``int64[3, K]`` on the GPU: row 0 ``#(pred==c & label==c)``, row 1 ``#(pred==c)``, row 2 ``#(label==c)``.
+
+    ``pred`` is a uint8 label map (any shape), ``label`` uint8 or integer-valued float32 of the same number of
+    voxels (the reference's loaders give float32 ``[1, 1, D, H, W]``).  Counts are ADDED into ``out`` when given.
+    """
+    if not (pred.is_cuda and label.is_cuda):
+        raise _lib.MssError("dice_counts needs CUDA tensors; there is no CPU fallback")
+    if n_classes > _lib.MAX_DICE_CLASSES:
+        raise _lib.MssError(f"dice_counts supports up to {_lib.MAX_DICE_CLASSES} classes")
+    pred = pred.contiguous()
+    if pred.dtype != torch.uint8:
+        pred = pred.to(torch.uint8)
+    if label.dtype == torch.uint8:
+        ldt = 0
+    else:
+        label = label.to(torch.float32)
+        ldt = 1
+    label = label.contiguous()
+    if pred.numel() != label.numel():
+        raise ValueError(f"pred has {pred.numel()} voxels, label {label.numel()}")
+    if out is None:
+        out = torch.zeros((3, n_classes), dtype=torch.int64, device=pred.device)
+    with torch.cuda.device(pred.device):
+        rc = _lib.load().mss_dice_counts(pred.data_ptr(), label.data_ptr(), ldt, pred.numel(), int(n_classes),
+                                         out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_dice_counts")
+    return out
+
+
+def dice_from_counts(counts: Any) -> np.ndarray:
+    """``2 TP / (Y + P)`` where ``Y > 0`` else NaN (MONAI compute_meandice), float64, per class (last axis)."""
+    c = counts.detach().cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)
+    tp, p, y = (c[..., i, :].astype(np.float64) for i in range(3))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = 2.0 * tp / (y + p)
+    return np.where(y > 0, d, np.nan)
+
+
+class DiceMeter:
+    """Per-volume Dice bookkeeping of engine/test.py:56-69: one ``[K]`` Dice vector per volume, class mean =
+    nanmean over volumes (NaN if the class never occurs), mDice = nanmean over classes."""
+
+    def __init__(self, n_classes: int) -> None:
+        self.k = n_classes
+        self.per_volume: List[np.ndarray] = []
+
+    def update(self, pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        counts = dice_counts(pred, label, self.k)
+        self.per_volume.append(counts.cpu().numpy())
+        return counts
+
+    def add_counts(self, counts: Any) -> None:
+        c = counts.detach().cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)
+        self.per_volume.extend(list(c.reshape(-1, 3, self.k)))
+
+    def class_means(self) -> Tuple[np.ndarray, float]:
+        d = np.stack([dice_from_counts(c) for c in self.per_volume]) if self.per_volume else np.full((1, self.k), np.nan)
+        means = np.full(self.k, np.nan)
+        for c in range(self.k):
+            col = d[:, c]
+            if np.any(~np.isnan(col)):
+                means[c] = np.nanmean(col)
+        m = float(np.nanmean(means)) if np.any(~np.isnan(means)) else float("nan")
+        return means, m

@@ -1,0 +1,147 @@
+"""GPU parity for the individual kernels: extraction, finalize, vote, dice, halo add."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import medicalsemseg_b200 as mss
+from medicalsemseg_b200 import _lib, inferer
+from medicalsemseg_b200.grid import make_grid
+from oracle import dice as odice
+from oracle import vote as ovote
+from tests.golden.cases import VOTE_CASES, make_vote_maps
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def extract_all(vol, roi, overlap, cval, use_tma, batch=3):
+    plan = inferer.get_plan(tuple(vol.shape[2:]), roi, overlap, vol.device, vol.shape[0])
+    imp = torch.ones(plan.grid.roi, device=vol.device)
+    st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LOGITS, sw_batch=batch, use_tma=use_tma)
+    patches, centers = [], []
+    for first in range(0, st.total, batch):
+        n = min(batch, st.total - first)
+        p, c = st.extract(vol, first, n, cval)
+        patches.append(p)
+        centers.append(c)
+    return plan.grid, torch.cat(patches), torch.cat(centers)
+
+
+@pytest.mark.parametrize("shape,roi,overlap,cval", [
+    ((1, 1, 40, 36, 44), 16, 0.25, 0.0),        # W % 4 == 0: TMA path
+    ((2, 3, 33, 40, 48), (16, 24, 32), 0.5, 0.0),
+    ((1, 1, 128, 112, 104), 96, 0.5, 0.0),      # the 96^3 box geometry, clamped starts 32/16/8
+    ((1, 2, 41, 37, 50), (24, 16, 32), 0.5, 0.0),  # W % 4 != 0: plain path
+    ((1, 1, 10, 40, 21), 16, 0.25, -0.697),     # padded: plain path with cval
+    ((1, 1, 30, 30, 30), (15, 10, 7), 0.3, 0.0),  # roi_w % 4 != 0
+])
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_extract_matches_slicing(shape, roi, overlap, cval, use_tma):
+    rs = np.random.RandomState(11)
+    vol = torch.from_numpy(rs.standard_normal(shape).astype(np.float32)).cuda()
+    g, patches, centers = extract_all(vol, roi, overlap, cval, use_tma)
+    pads = []
+    for a in (2, 1, 0):
+        diff = g.image_size[a] - g.orig_size[a]
+        pads.extend([diff // 2, diff - diff // 2])
+    padded = torch.nn.functional.pad(vol, pads, value=cval)
+    i = 0
+    for b in range(shape[0]):
+        for n in range(g.n_windows):
+            s = g.window_start(n)
+            want = padded[b, :, s[0]:s[0] + g.roi[0], s[1]:s[1] + g.roi[1], s[2]:s[2] + g.roi[2]]
+            assert torch.equal(patches[i], want), (b, n, s)
+            want_c = torch.tensor(g.centers(n)).float()  # double division rounded once, engine/utils.py:126-130
+            assert torch.equal(centers[i].cpu(), want_c)
+            i += 1
+    assert i == patches.shape[0]
+
+
+@pytest.mark.parametrize("name", sorted(VOTE_CASES))
+def test_majority_vote_bit_exact(name):
+    case = VOTE_CASES[name]
+    maps = make_vote_maps(case)
+    want = ovote.majority_vote(maps, case["k"])
+    got = mss.majority_vote([torch.from_numpy(m).cuda() for m in maps], case["k"])
+    assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(np.load(os.path.join(GOLD, f"vote_{name}.npz"))["voted"], got.cpu().numpy())
+    # reference call convention: tuple of float64 arrays (nibabel get_fdata), int64 result
+    new = mss.get_new_label(tuple(m.astype(np.float64) for m in maps), len(maps), case["k"])
+    assert new.dtype == np.int64 and np.array_equal(new.astype(np.uint8), want)
+
+
+def test_majority_vote_unaligned_and_large():
+    rs = np.random.RandomState(5)
+    for n in (1, 15, 17, 1000003):
+        maps = [rs.randint(0, 5, size=n + 1).astype(np.uint8) for _ in range(5)]
+        dev = [torch.from_numpy(m).cuda()[1:] for m in maps]  # odd base address: scalar path
+        want = ovote.majority_vote([m[1:] for m in maps], 5)
+        assert np.array_equal(mss.majority_vote(dev, 5).cpu().numpy(), want)
+    v = 240 * 240 * 155  # BASELINE.json configs[3] shape
+    maps = [rs.randint(0, 3, size=v).astype(np.uint8) for _ in range(5)]
+    got = mss.majority_vote([torch.from_numpy(m).cuda() for m in maps], 3).cpu().numpy()
+    assert np.array_equal(got, ovote.majority_vote_rule(maps, 3))
+
+
+@pytest.mark.parametrize("k,n,ldt", [(14, 100003, "u8"), (14, 100003, "f32"), (3, 17, "u8"), (16, 4096, "f32"),
+                                     (2, 1 << 22, "u8"), (14, 512 * 512 * 50, "u8")])
+def test_dice_counts_bit_exact(k, n, ldt):
+    rs = np.random.RandomState(k + n % 97)
+    pred = rs.randint(0, k + 2, size=n).astype(np.uint8)   # values >= k must be counted nowhere
+    lab = rs.randint(0, k + 1, size=n).astype(np.uint8)
+    lab_t = torch.from_numpy(lab).cuda() if ldt == "u8" else torch.from_numpy(lab.astype(np.float32)).cuda()
+    got = mss.dice_counts(torch.from_numpy(pred).cuda(), lab_t, k)
+    want = odice.dice_counts(pred, lab, k)
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+    assert np.allclose(mss.dice_from_counts(got), odice.dice_from_counts(want), equal_nan=True)
+    # accumulating into an existing buffer adds
+    again = mss.dice_counts(torch.from_numpy(pred).cuda(), lab_t, k, out=got)
+    assert np.array_equal(again.cpu().numpy(), 2 * want)
+
+
+def test_dice_meter_follows_reference_nan_rules():
+    k = 4
+    meter = mss.DiceMeter(k)
+    pred = torch.tensor([0, 1, 1, 2, 2, 2], dtype=torch.uint8).cuda()
+    lab = torch.tensor([0, 1, 2, 2, 2, 0], dtype=torch.float32).cuda().reshape(1, 1, 1, 2, 3)
+    meter.update(pred, lab)
+    meter.update(pred, lab)
+    means, m = meter.class_means()
+    want, want_m = odice.class_means(np.stack([odice.dice_from_counts(odice.dice_counts(pred.cpu().numpy(), lab.cpu().numpy(), k))] * 2))
+    assert np.allclose(means, want, equal_nan=True) and m == pytest.approx(want_m)
+    assert np.isnan(means[3])
+
+
+def test_halo_add():
+    lib = _lib.load()
+    a = torch.randn(6, 40, device="cuda")
+    b = torch.randn(6, 48, device="cuda")
+    want = a.clone()
+    want[:, :32] += b[:, :32]
+    rc = lib.mss_halo_add(a.data_ptr(), 40, b.data_ptr(), 48, 6, 32, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and torch.equal(a, want)
+    a2 = torch.randn(5, 7, device="cuda")
+    b2 = torch.randn(5, 7, device="cuda")
+    want2 = a2 + b2
+    assert lib.mss_halo_add(a2.data_ptr(), 7, b2.data_ptr(), 7, 5, 7, torch.cuda.current_stream().cuda_stream) == 0
+    assert torch.equal(a2, want2)
+
+
+def test_logits_to_labels_probs_and_ties():
+    rs = np.random.RandomState(3)
+    logits = torch.from_numpy(rs.standard_normal((2, 5, 9, 10, 13)).astype(np.float32)).cuda()
+    logits[0, 1, 0, 0, 0] = logits[0, 3, 0, 0, 0] = 7.0      # exact tie: first maximum wins
+    logits[1, :, 2, 3, 4] = float("nan")                        # NaN rows: softmax is all-NaN, np.argmax answers 0
+    logits[1, 3, 4, 4, 4] = float("nan")
+    logits[1, 2, 5, 5, 5] = float("inf")
+    st = mss.InferStats()
+    labels, probs = mss.logits_to_labels(logits, return_probs=True, stats=st)
+    want = np.argmax(torch.softmax(logits, 1).cpu().numpy(), axis=1).astype(np.uint8)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert labels[0, 0, 0, 0].item() == 1 and labels[1, 2, 3, 4].item() == 0 and labels[1, 4, 4, 4].item() == 0
+    ok = ~torch.isnan(logits).any(1, keepdim=True).expand_as(logits)
+    assert torch.allclose(probs[ok], torch.softmax(logits, 1)[ok], rtol=1e-5, atol=1e-7)
+    assert st.near_ties >= 1

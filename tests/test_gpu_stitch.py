@@ -1,0 +1,175 @@
+"""GPU parity: the CUDA stitching path (through the C ABI) against the oracle on the same seeded inputs,
+and against the fixtures the reference itself produced (tests/golden)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import medicalsemseg_b200 as mss
+from medicalsemseg_b200 import importance as I
+from oracle import monai08 as M
+from oracle import sliding_window as osw
+from oracle.predictors import ArithmeticPredictor
+from tests.golden.cases import SW_CASES, make_volume
+from tests.gpu_helpers import TOL, assert_labels_match, cuda_inputs, oracle_run, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = [n for n in sorted(SW_CASES) if n != "cfg1_geometry"]
+
+
+@pytest.mark.parametrize("roi", [(96, 96, 96), (16, 16, 16), (24, 16, 32), (8, 12, 20), (5, 7, 9)])
+def test_importance_map_bit_exact_with_host_taps(roi):
+    want = M.compute_importance_map(roi, mode="gaussian", sigma_scale=0.125)
+    got = I.importance_map(roi, "gaussian", 0.125, "cuda").cpu()
+    assert torch.equal(got, want)
+    ones = I.importance_map(roi, "constant", 0.125, "cuda").cpu()
+    assert torch.equal(ones, torch.ones(roi))
+
+
+def test_importance_map_device_taps_and_v12():
+    roi = (96, 96, 96)
+    want = M.compute_importance_map(roi, mode="gaussian", sigma_scale=0.125)
+    dev = I.importance_map(roi, "gaussian", 0.125, "cuda", taps="device").cpu()
+    # float32 erf differs by an ulp between CPU and GPU; erf(a)-erf(b) near 1 amplifies it in the tails
+    assert torch.allclose(dev, want, rtol=5e-3, atol=0)
+    c = slice(24, 72)
+    assert torch.allclose(dev[c, c, c], want[c, c, c], rtol=2e-5, atol=0)
+    v12 = I.importance_map((24, 16, 32), "gaussian", 0.125, "cuda", variant="monai12").cpu()
+    assert torch.equal(v12, M.compute_importance_map_v12((24, 16, 32)))
+    v12d = I.importance_map((24, 16, 32), "gaussian", 0.125, "cuda", variant="monai12", taps="device").cpu()
+    assert torch.allclose(v12d, M.compute_importance_map_v12((24, 16, 32)), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_compat_logits_bit_exact_vs_oracle(name):
+    """sliding_window_inference (reference signature): same per-window logits, same weights -> identical floats."""
+    case = SW_CASES[name]
+    ref, ref_pred = oracle_run(case)
+    vol, affine = cuda_inputs(case)
+    pred = ArithmeticPredictor(case["k"])
+    st = mss.InferStats()
+    out = mss.sliding_window_inference(vol, affine, case["roi"], case["sw_batch"], pred, overlap=case["overlap"],
+                                       mode=case["mode"], cval=case.get("cval", 0.0), mss_stats=st)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert pred.calls == ref_pred.calls  # same batches, same centre shapes (quirks Q3, Q10)
+    got = out.cpu()
+    assert rel_err(got, ref) <= TOL
+    assert torch.equal(got, ref), f"max abs diff {(got - ref).abs().max().item()}"
+    # and the fixture the reference produced in the build container
+    fx = np.load(os.path.join(GOLD, f"sw_{name}.npz"))
+    gold = json.load(open(os.path.join(GOLD, "manifest.json")))["sliding_window"][name]
+    sample = fx["logits"].reshape(-1) if gold["stored"] == "full" else fx["sample"]
+    mine = got.contiguous().numpy().reshape(-1)
+    mine = mine if gold["stored"] == "full" else mine[::997]
+    assert np.allclose(mine, sample, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("group_bytes", [None, 1])
+def test_fused_labels_vs_oracle(name, group_bytes):
+    """sliding_window_infer (labels straight from the accumulate kernel); group_bytes=1 forces one
+    accumulate launch per predictor batch, i.e. the accumulator read-modify-write path."""
+    case = SW_CASES[name]
+    ref, _ = oracle_run(case)
+    vol, affine = cuda_inputs(case)
+    st = mss.InferStats()
+    labels = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), case["roi"], case["overlap"], case["mode"],
+                                      sw_batch_size=case["sw_batch"], cval=case.get("cval", 0.0), affine=affine,
+                                      stats=st, group_bytes=group_bytes)
+    assert tuple(labels.shape) == (case["shape"][0],) + tuple(case["shape"][2:])
+    mism = assert_labels_match(labels, ref)
+    assert mism <= 2  # identical logits -> identical labels unless softmax rounding merges a near-tie
+    if group_bytes is None:
+        assert st.n_accumulate_calls == 1 and not st.accumulator_allocated
+    else:
+        assert st.n_accumulate_calls == st.n_predictor_calls
+        assert st.accumulator_allocated == (st.n_predictor_calls > 1)
+
+
+@pytest.mark.parametrize("name", ["aniso_ragged", "two_volumes", "padded_cval", "brats_like"])
+def test_labels_and_logits_together(name):
+    case = SW_CASES[name]
+    ref, _ = oracle_run(case)
+    vol, affine = cuda_inputs(case)
+    labels, logits = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), case["roi"], case["overlap"],
+                                              case["mode"], sw_batch_size=case["sw_batch"], cval=case.get("cval", 0.0),
+                                              affine=affine, return_logits=True, group_bytes=1)
+    assert torch.equal(logits.cpu(), ref)
+    assert assert_labels_match(labels, ref) == 0
+    again = mss.logits_to_labels(logits.contiguous())
+    assert torch.equal(again, labels.contiguous())
+
+
+def test_plain_tensor_predictor_inferer_object():
+    """run_evaluation.py:68-74 convention: SlidingWindowInferer hands the network the plain patch tensor (quirk Q6)."""
+    case = SW_CASES["constant_mode"]
+    ref, ref_pred = oracle_run(case, tuple_input=False)
+    vol, _ = cuda_inputs(case)
+    pred = ArithmeticPredictor(case["k"])
+    inferer = mss.SlidingWindowInferer(roi_size=case["roi"], sw_batch_size=case["sw_batch"], overlap=case["overlap"],
+                                       mode=case["mode"], cval=0.0)
+    out = inferer(inputs=vol, network=pred)
+    assert pred.calls == ref_pred.calls and all(c[1] is None for c in pred.calls)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_half_precision_logits_accumulate_in_fp32():
+    """Under autocast the predictor returns fp16/bf16; engine/utils.py:147 promotes to fp32 before weighting."""
+    case = SW_CASES["overlap_075"]
+    for dt in (torch.float16, torch.bfloat16):
+        class Half(ArithmeticPredictor):
+            def __call__(self, x, *a, **k):
+                return super().__call__(x, *a, **k).to(dt)
+        vol = torch.from_numpy(make_volume(case))
+        affine = torch.tensor([[1.5, 1.5, 2.0]], dtype=torch.float32)
+        ref = osw.sliding_window_inference(vol, affine, case["roi"], case["sw_batch"], Half(case["k"]),
+                                           overlap=case["overlap"], mode=case["mode"])
+        out = mss.sliding_window_inference(vol.cuda(), affine.cuda(), case["roi"], case["sw_batch"], Half(case["k"]),
+                                           overlap=case["overlap"], mode=case["mode"])
+        assert torch.equal(out.cpu(), ref)
+
+
+def test_non_constant_padding_modes():
+    case = dict(SW_CASES["padded_cval"])
+    vol, affine = cuda_inputs(case)
+    for pm in ("reflect", "replicate", "circular"):
+        ref = osw.sliding_window_inference(vol.cpu(), affine.cpu(), case["roi"], case["sw_batch"],
+                                           ArithmeticPredictor(case["k"]), overlap=case["overlap"], mode=case["mode"],
+                                           padding_mode=pm)
+        out = mss.sliding_window_inference(vol, affine, case["roi"], case["sw_batch"], ArithmeticPredictor(case["k"]),
+                                           overlap=case["overlap"], mode=case["mode"], padding_mode=pm)
+        assert torch.equal(out.cpu(), ref), pm
+
+
+def test_cfg1_geometry_128_cube_roi96():
+    """BASELINE.json configs[0] stitching geometry (128^3, roi 96^3, overlap .25, K=14, N=8) incl. the TMA extract."""
+    case = SW_CASES["cfg1_geometry"]
+    ref, _ = oracle_run(case)
+    vol, affine = cuda_inputs(case)
+    st = mss.InferStats()
+    out = mss.sliding_window_inference(vol, affine, case["roi"], case["sw_batch"], ArithmeticPredictor(case["k"]),
+                                       overlap=case["overlap"], mode=case["mode"], mss_stats=st)
+    assert st.n_windows == 8
+    assert torch.equal(out.cpu(), ref)
+    labels = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), 96, case["overlap"], "gaussian",
+                                      sw_batch_size=case["sw_batch"], affine=affine)
+    assert assert_labels_match(labels, ref) == 0
+    gold = json.load(open(os.path.join(GOLD, "manifest.json")))["sliding_window"]["cfg1_geometry"]
+    fx = np.load(os.path.join(GOLD, "sw_cfg1_geometry.npz"))
+    assert np.allclose(out.cpu().contiguous().numpy().reshape(-1)[::997], fx["sample"], rtol=1e-5, atol=1e-6)
+    assert gold["shape"] == list(out.shape)
+
+
+def test_argument_errors_match_reference():
+    vol = torch.zeros(1, 1, 20, 20, 20, device="cuda")
+    with pytest.raises(AssertionError, match="overlap must be >= 0 and < 1."):
+        mss.sliding_window_inference(vol, None, 16, 1, lambda x: x[0], overlap=1.0)
+    with pytest.raises(ValueError):
+        mss.sliding_window_inference(vol, None, (16, 16), 1, lambda x: x[0])
+    with pytest.raises(ValueError):
+        mss.sliding_window_inference(vol, None, 16, 1, lambda x: x[0], padding_mode="nearest")
+    with pytest.raises(ValueError):  # predictor returning the wrong spatial shape
+        mss.sliding_window_inference(vol, None, 16, 1, lambda x: x[0][..., :8])
