@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: voxels/s of sliding-window inference (ROI 96^3, overlap 0.5, gaussian), BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = one full pass of the hot path over one synthetic volume: every window extracted, the backbone run on
+every patch batch, all logits stitched, labels produced.  Workloads (BASELINE.json configs):
+
+    btcv       cfg2  1x1x512x512x200, Swin-UNETR-style backbone, K=14, N=400 windows     (default)
+    wholebody  cfg3  1x1x512x512x1024, z-slab partitioned across the ranks, N=2100       (--workload wholebody)
+    brats      cfg4  1x4x240x240x155, K=3, one model per rank -> majority vote
+    cfg1             1x1x128^3, UNet, overlap .25, N=8
+
+With N > 1 ranks the default shards VOLUMES (cfg5: one btcv volume per rank and step, Dice counts all-reduced;
+no data-path collective, "scaling": "weak"); --workload wholebody partitions ONE volume into slabs with a halo
+exchange ("strong").  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "btcv": dict(shape=(1, 1, 512, 512, 200), k=14, backbone="swin_unetr", overlap=0.5, cfg="configs[1]"),
+    "wholebody": dict(shape=(1, 1, 512, 512, 1024), k=14, backbone="swin_unetr", overlap=0.5, cfg="configs[2]"),
+    "brats": dict(shape=(1, 4, 240, 240, 155), k=3, backbone="swin_unetr", overlap=0.5, cfg="configs[3]"),
+    "cfg1": dict(shape=(1, 1, 128, 128, 128), k=14, backbone="unet", overlap=0.25, cfg="configs[0]"),
+}
+ROI = 96
+METRIC = "voxels/sec sliding-window inference (ROI 96^3, ov 0.5)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms through NVML while the timed region runs."""
+
+    def __init__(self, index: int) -> None:
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, threading.Event(), [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self) -> None:
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self) -> dict:
+        self.stop_flag.set()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:  # noqa: BLE001
+            return local
+    return local
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port of engine/utils.py + engine/test.py:140-141), bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+
+def cpu_reference_sample(wl: dict, repeats: int, warmup: int):
+    """Times the oracle on a strip of the workload holding `n_s` windows with the same backbone on the host cores and
+    extrapolates to the full volume: T_full = T_stitch+backbone * (N / n_s) + T_labels * (V / V_s)."""
+    from benchmarks.backbones import build_backbone
+    from oracle import sliding_window as osw
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nb, cin, d, h, w = wl["shape"]
+    sd, sh = min(d, ROI), min(h, ROI)
+    sample_shape = (1, cin, sd, sh, w)  # one row of windows along W
+    model = build_backbone(wl["backbone"], cin, wl["k"])
+    rs = np.random.RandomState(0)
+    vol = torch.from_numpy(rs.standard_normal(sample_shape).astype(np.float32))
+    affine = torch.ones(1, 3)
+    _, starts = osw.window_grid((d, h, w), (ROI,) * 3, wl["overlap"])
+    n_full = len(starts[0]) * len(starts[1]) * len(starts[2])
+    _, s_starts = osw.window_grid(sample_shape[2:], (ROI,) * 3, wl["overlap"])
+    n_s = len(s_starts[0]) * len(s_starts[1]) * len(s_starts[2])
+    v_full, v_s = d * h * w, sd * sh * w
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + repeats):
+            t0 = time.perf_counter()
+            out = osw.sliding_window_inference(vol, affine, ROI, 4, model, overlap=wl["overlap"], mode="gaussian")
+            t1 = time.perf_counter()
+            osw.labels_from_logits(out)
+            t2 = time.perf_counter()
+            if it >= warmup:
+                times.append((t1 - t0) * (n_full / n_s) + (t2 - t1) * (v_full / v_s))
+    t_full = float(np.mean(times))
+    sample = (f"oracle (port of engine/utils.py + engine/test.py:140-141) with the same {wl['backbone']} backbone on a "
+              f"{sd}x{sh}x{w} strip = {n_s} of {n_full} windows, torch {cores} threads; per-window time scaled by "
+              f"{n_full}/{n_s}, label time by voxels (extrapolated)")
+    return v_full / t_full, t_full, cores, sample
+
+
+def run_reference(args, wl) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, t_full, cores, sample = cpu_reference_sample(wl, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "shape": list(wl["shape"]), "roi": ROI,
+                                                        "overlap": wl["overlap"], "classes": wl["k"], "blend": "gaussian"},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="btcv", choices=sorted(WORKLOADS))
+    ap.add_argument("--sw-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--group-gib", type=float, default=None, help="logits held per accumulate launch (default: auto)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import medicalsemseg_b200 as mss
+    from benchmarks.backbones import build_backbone
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "wholebody" and world > 1:
+        from benchmarks.slab_bench import run_wholebody
+        run_wholebody(args, wl, rank, world, dev, dist)
+        return
+
+    nb, cin, d, h, w = wl["shape"]
+    k = wl["k"]
+    model = build_backbone(wl["backbone"], cin, k).to(dev)
+    gen = torch.Generator().manual_seed(rank)  # rank 0 = the seed-0 volume of SURVEY.md section 8d
+    host_vol = torch.randn(wl["shape"], generator=gen).pin_memory()
+    dev_vol = host_vol.to(dev)
+    host_labels = torch.empty((nb, d, h, w), dtype=torch.uint8).pin_memory()
+    label_gt = (torch.arange(d * h * w, device=dev) // 4096 % k).to(torch.uint8).view(d, h, w)  # for the Dice leg (N>1)
+    group_bytes = None if args.group_gib is None else int(args.group_gib * (1 << 30))
+    v = nb * d * h * w
+
+    def step(volume, stats=None, time_kernels=False):
+        with torch.no_grad():
+            return mss.sliding_window_infer(volume, model, ROI, wl["overlap"], "gaussian", sw_batch_size=args.sw_batch,
+                                            stats=stats, time_kernels=time_kernels, group_bytes=group_bytes)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dice_leg(labels):
+        if dist is None:
+            return
+        counts = mss.dice_counts(labels[0], label_gt, k)
+        dist.all_reduce(counts)
+
+    for _ in range(args.warmup):
+        dice_leg(step(dev_vol))
+    barrier()
+
+    # --- timed region 1: inputs resident in HBM ------------------------------------------------------------------
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    stats = [mss.InferStats() for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for s in range(args.steps):
+        dice_leg(step(dev_vol, stats[s], time_kernels=True))
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+
+    # --- timed region 2: end to end through the public API with host buffers ---------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        labels = step(host_vol.to(dev, non_blocking=True))
+        dice_leg(labels)
+        host_labels.copy_(labels, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.result()
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kms = [s.kernel_ms() for s in stats]
+        acc_launch_ms = [x for s in stats for x in s.kernel_launch_ms("accumulate")]
+        n_win = stats[0].n_windows
+        r = ROI**3
+        n_acc = max(stats[0].n_accumulate_calls, 1)
+        # algorithmic bytes of the accumulate kernel as built: every logit read once (4 N K R), plus the
+        # uint8 label of every voxel written once; a launch that does not hold all windows also reads+writes its
+        # share of the fp32 accumulator (8 V K per extra pass, upper bound).
+        acc_bytes = 4 * n_win * k * r + v + (8 * v * k * (n_acc - 1) if n_acc > 1 else 0)
+        acc_ms_step = float(np.mean([m.get("accumulate", 0.0) for m in kms]))
+        achieved = acc_bytes / (acc_ms_step * 1e-3) / 1e9 if acc_ms_step > 0 else None
+        line = {
+            "metric": METRIC, "value": v * world * args.steps / (ms_total * 1e-3), "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "baseline_config": wl["cfg"], "shape": list(wl["shape"]), "roi": ROI,
+                "overlap": wl["overlap"], "classes": k, "blend": "gaussian", "windows": n_win, "sw_batch": args.sw_batch,
+                "backbone": wl["backbone"] + " (random init, seed 13, fp32 eager torch)", "volumes_per_step": world,
+                "l2_policy": "inputs larger than L2: 19.8 GB of logits per step stream through the 126 MB L2",
+                "sharding": "one volume per rank, Dice counts all-reduced (cfg5 style)" if world > 1 else "single GPU",
+            },
+            "e2e": {"value": v * world * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
+                    "h2d_bytes_per_step": host_vol.numel() * 4, "d2h_bytes_per_step": host_labels.numel()},
+            "gpu_launches": int(sum(s.gpu_launches for s in stats)),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "accumulate_kernel<float> (fused normalise+argmax)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "algorithmic_bytes_per_launch": acc_bytes / n_acc, "launches_per_step": n_acc,
+                "avg_launch_ms": float(np.mean(acc_launch_ms)) if acc_launch_ms else None,
+                "survey_formula_gbs": (12 * n_win * k * r / (acc_ms_step * 1e-3) / 1e9) if acc_ms_step > 0 else None,
+            },
+            "breakdown_ms_per_step": {name: float(np.mean([m.get(name, 0.0) for m in kms])) for name in
+                                      ("predictor", "extract", "accumulate", "finalize")},
+            "volumes_per_s": world * args.steps / (ms_total * 1e-3),
+        }
+        ext_ms = line["breakdown_ms_per_step"]["extract"]
+        if ext_ms > 0:
+            line["roofline_extract"] = {"achieved": 8 * n_win * cin * r / (ext_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                        "note": "sum over per-batch launches (7 MB each: launch-latency bound)"}
+        if not args.no_cpu_baseline:
+            val, t_full, cores, sample = cpu_reference_sample(wl, repeats=1, warmup=0)
+            line["cpu_baseline"] = {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

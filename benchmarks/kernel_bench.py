@@ -1,0 +1,198 @@
+#!/usr/bin/env python
+"""Per-kernel roofline harness: every non-backbone kernel of libmss_b200.so on BASELINE.json shapes, timed with CUDA
+events on the launching stream (warm-up, L2 flushed between timed launches), reported as achieved GB/s of ALGORITHMIC
+bytes against the measured HBM peak.  No backbone involved: logits are synthetic and resident.
+
+    python benchmarks/kernel_bench.py [--only accumulate,extract,...] [--reps 5] [--shape btcv|brats|small]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import medicalsemseg_b200 as mss  # noqa: E402
+from medicalsemseg_b200 import _lib, inferer  # noqa: E402
+from medicalsemseg_b200.importance import importance_map  # noqa: E402
+
+SHAPES = {
+    "btcv": dict(shape=(1, 1, 512, 512, 200), k=14, m=5),
+    "brats": dict(shape=(1, 4, 240, 240, 155), k=3, m=5),
+    "small": dict(shape=(1, 1, 192, 192, 200), k=14, m=5),
+}
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+
+
+class Flusher:
+    def __init__(self, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1)  # 256 MB > 126 MB L2
+
+
+def timed(fn, reps, flush):
+    fn()
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--shape", default="btcv", choices=sorted(SHAPES))
+    ap.add_argument("--sw-batch", type=int, default=4)
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    cfg = SHAPES[args.shape]
+    nb, cin, d, h, w = cfg["shape"]
+    k, m = cfg["k"], cfg["m"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    flush = Flusher(dev)
+    pk = peak()
+    results = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    v = d * h * w
+    r = 96**3
+
+    def report(name, bytes_, ms_med, ms_min, note=""):
+        gbs = bytes_ / (ms_med * 1e-3) / 1e9
+        results[name] = dict(ms=ms_med, ms_min=ms_min, gb=bytes_ / 1e9, gbs=gbs, frac=gbs / pk, note=note)
+        print(f"{name:34s} {ms_med:9.3f} ms  {bytes_ / 1e9:8.3f} GB  {gbs:8.1f} GB/s  {gbs / pk * 100:5.1f}% of measured peak  {note}",
+              flush=True)
+
+    def want(name):
+        return not only or name in only
+
+    plan = inferer.get_plan((d, h, w), 96, 0.5, dev, nb)
+    imp = importance_map((96, 96, 96), "gaussian", 0.125, dev)
+    n_win = plan.grid.n_windows
+    B = args.sw_batch
+    vol = torch.randn(cfg["shape"], device=dev)
+
+    if want("importance"):
+        def f():
+            inferer.build_importance_map.__globals__["_CACHE"].clear()
+            importance_map((96, 96, 96), "gaussian", 0.125, dev)
+        med, mn = timed(f, args.reps, flush)
+        report("importance_map 96^3 (3 launches)", 4 * r, med, mn, "includes host taps + 3 tiny H2D copies")
+
+    if want("extract"):
+        st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LABELS, sw_batch=B)
+        for tma in (True, False):
+            st.use_tma = tma
+            med, mn = timed(lambda: st.extract(vol, 0, B, 0.0), args.reps, flush)
+            report(f"extract B={B} tma={int(tma)}", 8 * B * cin * r, med, mn, "one predictor batch")
+        big = 40
+        st.use_tma = True
+        med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
+        report(f"extract B={big} tma=1", 8 * big * cin * r, med, mn)
+        st.use_tma = False
+        med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
+        report(f"extract B={big} tma=0", 8 * big * cin * r, med, mn)
+
+    if want("accumulate") or want("accumulate_rmw") or want("finalize"):
+        n_batches = -(-n_win // B)
+        logits = [torch.randn((min(B, n_win - i * B), k, 96, 96, 96), device=dev) for i in range(n_batches)]
+        lay = plan.layout(k)
+        labels = torch.empty((nb, d, h, w), dtype=torch.uint8, device=dev)
+        near = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def acc_call(first_b, nbatch, acc, fuse):
+            ptrs = (C.c_void_p * nbatch)(*[t.data_ptr() for t in logits[first_b:first_b + nbatch]])
+            nw = sum(t.shape[0] for t in logits[first_b:first_b + nbatch])
+            rc = lib.mss_accumulate(C.byref(lay), ptrs, nbatch, B, _lib.MSS_F32, first_b * B, nw, imp.data_ptr(),
+                                    None if acc is None else acc.data_ptr(), fuse, labels.data_ptr(), w, 1e-5,
+                                    near.data_ptr(), stream)
+            _lib.check(rc, "mss_accumulate")
+
+        if want("accumulate"):
+            chunks = [(i, min(_lib.MAX_BATCH_PTRS, n_batches - i)) for i in range(0, n_batches, _lib.MAX_BATCH_PTRS)]
+            if len(chunks) == 1:
+                med, mn = timed(lambda: acc_call(0, n_batches, None, _lib.FUSE_LABELS), args.reps, flush)
+                report("accumulate fused->labels, 1 launch", 4 * n_win * k * r + v, med, mn, f"{n_win} windows, K={k}")
+            acc = torch.empty((nb, k, d, h, plan.pitch_w), device=dev)
+            med, mn = timed(lambda: acc_call(0, n_batches, acc, _lib.FUSE_LOGITS), args.reps, flush) if len(chunks) == 1 else (0, 0)
+            if len(chunks) == 1:
+                report("accumulate fused->logits, 1 launch", 4 * n_win * k * r + 4 * v * k, med, mn)
+        if want("accumulate_rmw"):
+            acc = torch.empty((nb, k, d, h, plan.pitch_w), device=dev)
+            per = max(1, plan.grid.n_starts[2])  # one W-row of windows per launch
+            gb = max(1, per // B)
+
+            def rmw():
+                for fb in range(0, n_batches, gb):
+                    acc_call(fb, min(gb, n_batches - fb), acc, _lib.FUSE_LOGITS)
+            med, mn = timed(rmw, max(2, args.reps // 2), flush)
+            report(f"accumulate per {gb * B}-window group (RMW)", 12 * n_win * k * r, med, mn,
+                   "SURVEY formula 12NKR (reference-shaped traffic)")
+        if want("finalize"):
+            acc = torch.randn((nb, k, d, h, plan.pitch_w), device=dev)
+            lo, hi = _lib.I3(0, 0, 0), _lib.I3(d, h, w)
+
+            def fin(norm):
+                rc = lib.mss_finalize_labels(C.byref(lay), acc.data_ptr(), imp.data_ptr(), norm, lo, hi, labels.data_ptr(), w,
+                                             None, None, 1e-5, near.data_ptr(), stream)
+                _lib.check(rc, "mss_finalize_labels")
+            med, mn = timed(lambda: fin(0), args.reps, flush)
+            report("finalize argmax", v * (4 * k + 1), med, mn)
+            med, mn = timed(lambda: fin(1), args.reps, flush)
+            report("finalize normalise+argmax", v * (4 * k + 1), med, mn)
+        del logits
+
+    if want("vote"):
+        maps = [torch.randint(0, k, (v,), dtype=torch.uint8, device=dev) for _ in range(m)]
+        med, mn = timed(lambda: mss.majority_vote(maps, k), args.reps, flush)
+        report(f"majority_vote M={m} K={k}", v * (m + 1), med, mn)
+
+    if want("dice"):
+        pred = torch.randint(0, k, (v,), dtype=torch.uint8, device=dev)
+        lab8 = torch.randint(0, k, (v,), dtype=torch.uint8, device=dev)
+        labf = lab8.float()
+        out = torch.zeros((3, k), dtype=torch.int64, device=dev)
+        med, mn = timed(lambda: mss.dice_counts(pred, lab8, k, out=out), args.reps, flush)
+        report(f"dice_counts u8 labels K={k}", 2 * v, med, mn)
+        med, mn = timed(lambda: mss.dice_counts(pred, labf, k, out=out), args.reps, flush)
+        report(f"dice_counts f32 labels K={k}", 5 * v, med, mn)
+
+    if want("halo"):
+        rows, length = k * 512, 512 * 48
+        a = torch.randn(rows, length, device=dev)
+        b = torch.randn(rows, length, device=dev)
+        med, mn = timed(lambda: _lib.check(lib.mss_halo_add(a.data_ptr(), length, b.data_ptr(), length, rows, length, stream),
+                                           "halo"), args.reps, flush)
+        report("halo_add 512x512x48xK", 12 * rows * length, med, mn)
+
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"kernel_bench_{args.shape}.json"), "w") as f:
+        json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

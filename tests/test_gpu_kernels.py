@@ -142,6 +142,6 @@ def test_logits_to_labels_probs_and_ties():
     want = np.argmax(torch.softmax(logits, 1).cpu().numpy(), axis=1).astype(np.uint8)
     assert np.array_equal(labels.cpu().numpy(), want)
     assert labels[0, 0, 0, 0].item() == 1 and labels[1, 2, 3, 4].item() == 0 and labels[1, 4, 4, 4].item() == 0
-    ok = ~torch.isnan(logits).any(1, keepdim=True).expand_as(logits)
+    ok = torch.isfinite(logits).all(1, keepdim=True).expand_as(logits)
     assert torch.allclose(probs[ok], torch.softmax(logits, 1)[ok], rtol=1e-5, atol=1e-7)
     assert st.near_ties >= 1

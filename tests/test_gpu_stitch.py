@@ -33,8 +33,9 @@ def test_importance_map_device_taps_and_v12():
     roi = (96, 96, 96)
     want = M.compute_importance_map(roi, mode="gaussian", sigma_scale=0.125)
     dev = I.importance_map(roi, "gaussian", 0.125, "cuda", taps="device").cpu()
-    # float32 erf differs by an ulp between CPU and GPU; erf(a)-erf(b) near 1 amplifies it in the tails
-    assert torch.allclose(dev, want, rtol=5e-3, atol=0)
+    # float32 erf differs by an ulp between CPU and GPU; erf(a)-erf(b) near 1 amplifies it to ~3e-3 relative per
+    # axis in the tails (three factors multiply) - the reason the default evaluates the taps with torch on the host
+    assert torch.allclose(dev, want, rtol=2e-2, atol=0)
     c = slice(24, 72)
     assert torch.allclose(dev[c, c, c], want[c, c, c], rtol=2e-5, atol=0)
     v12 = I.importance_map((24, 16, 32), "gaussian", 0.125, "cuda", variant="monai12").cpu()
