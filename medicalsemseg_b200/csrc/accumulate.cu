@@ -1,16 +1,22 @@
 // Weighted overlap accumulation with fused normalise / argmax
 // (replaces the Python scatter loop of engine/utils.py:137-151 and, when fused, engine/test.py:140-141).
 //
-// Output-stationary: one thread owns 4 consecutive W voxels of the stitched volume for all classes.
-// It walks the windows of THIS call that cover its voxels in ascending window order (the order of
-// engine/utils.py:146-148) and performs acc = fadd_rn(acc, fmul_rn(w, logit)) per window - the same
-// two roundings as `output_image[idx] += importance_map * seg_prob[i]`, so sums are bit-identical to
-// the reference's.  No atomics: every accumulator element has exactly one writer per launch.  The
-// accumulator is read only if a window of an earlier call touched the voxel (no memset needed) and
-// written once; a voxel whose last covering window is in this call is finished on the spot
-// (divide by the weight count, optionally argmax to uint8) and never travels through HBM again.
+// Output-stationary: one thread owns 4 consecutive W voxels of the stitched volume for all classes; a
+// CTA owns a tile of one D-plane (a few H rows x up to 128 W voxels).  The CTA first lists, in shared
+// memory, the windows of the grid that intersect its tile (ascending window index, i.e. the order of
+// engine/utils.py:146-148) with a ready-made base pointer per window, so the per-voxel inner loop is
+// nothing but {coverage test, one 16-byte weight load, K 16-byte logit loads, fmul_rn + fadd_rn}.
+// acc = fadd_rn(acc, fmul_rn(w, logit)) are the same two roundings as
+// `output_image[idx] += importance_map * seg_prob[i]`, so sums are bit-identical to the reference's.
+// No atomics: every accumulator element has exactly one writer per launch.  The accumulator is read
+// only if a window of an earlier launch touched the voxel (no memset needed) and written once; a voxel
+// whose last covering window is in this launch is finished on the spot (divide by the weight count, or
+// argmax straight to uint8) and never travels through HBM again.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "labels.cuh"
@@ -18,7 +24,7 @@
 namespace mss {
 
 constexpr int kAccThreads = 128;
-constexpr int kAccTK = 8;  // classes held in registers at a time
+constexpr int kMaxCand = 64;  // windows listed per shared-memory chunk
 
 struct AccParams {
     Geo g;
@@ -34,9 +40,11 @@ struct AccParams {
     unsigned long long* near_ties;
     int box_lo[3];  // local box this launch covers; box_lo[2] is a multiple of 4
     int box_n[3];
-    int nq;    // quads per row of the box
-    int b_lo;  // first volume touched
-    int vec_ok;  // logits pointers and roi allow 16-byte (8-byte for 16-bit logits) vector loads
+    int nq;        // quads per row of the box
+    int tq, th;    // tile: quads per row, rows
+    int n_wtiles;  // tiles along W
+    int b_lo;      // first volume touched
+    int vec_ok;    // logits pointers and roi allow 16-byte (8-byte for 16-bit logits) vector loads
 };
 
 template <typename LT>
@@ -68,95 +76,237 @@ struct LogitLoad<__nv_bfloat16> {
 
 __device__ __forceinline__ float& comp(float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
 
+enum : int { kBefore = 0, kNow = 1, kAfter = 2 };
+
+// ---- per-thread asynchronous copies into the thread's own shared-memory ring slots -----------------------
+// (shared-memory operands are 32-bit shared-window addresses computed once per thread)
+__device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(unsigned smem) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem));
+    return r;
+}
+__device__ __forceinline__ uint2 lds_u2(unsigned smem) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem));
+    return r;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <typename LT>
-__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const __grid_constant__ AccParams p) {
+struct Slot;  // one thread's 4 logits of one class in the ring
+template <>
+struct Slot<float> {
+    static constexpr int kBytes = 16;
+    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async16(s, g); }
+    static __device__ __forceinline__ float4 read(unsigned s) { return lds_f4(s); }
+};
+template <>
+struct Slot<__half> {
+    static constexpr int kBytes = 8;
+    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
+    static __device__ __forceinline__ float4 read(unsigned s) {
+        const uint2 r = lds_u2(s);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <>
+struct Slot<__nv_bfloat16> {
+    static constexpr int kBytes = 8;
+    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
+    static __device__ __forceinline__ float4 read(unsigned s) {
+        const uint2 r = lds_u2(s);
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                           __uint_as_float(r.y & 0xffff0000u));
+    }
+};
+
+template <typename LT, int KC, int S>
+constexpr size_t acc_smem_bytes() {
+    return static_cast<size_t>(S) * kAccThreads * (16 + KC * Slot<LT>::kBytes);
+}
+
+// KC classes are held in registers per pass; S ring stages (windows) are in flight per thread.
+template <typename LT, int KC, int S, int MINB>
+__global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __grid_constant__ AccParams p) {
+    extern __shared__ __align__(16) unsigned char ring[];  // [S][128] weights (float4) then [S][KC][128] logit slots
+    __shared__ const LT* s_ptr[kMaxCand];  // logits of class 0 such that ptr[gh * rw + gw] is voxel (gd, gh, gw)
+    __shared__ int s_wofs[kMaxCand];       // same re-basing for the importance map
+    __shared__ int s_sh[kMaxCand], s_sw[kMaxCand], s_cls[kMaxCand];
+    __shared__ int s_any_now;
+    constexpr int IB = Slot<LT>::kBytes;
+
     const Geo& g = p.g;
-    const int t = blockIdx.x * kAccThreads + threadIdx.x;
-    if (t >= p.nq * p.box_n[1]) return;
-    const int q = t % p.nq;
-    const int ld = p.box_lo[0] + blockIdx.y;
-    const int lh = p.box_lo[1] + t / p.nq;
-    const int lw = p.box_lo[2] + q * 4;
-    const int b = p.b_lo + blockIdx.z;
-    const int gd = ld + g.org[0], gh = lh + g.org[1], gw = lw + g.org[2];
+    const int tid = threadIdx.x;
     const int rd = g.roi[0], rh = g.roi[1], rw = g.roi[2];
     const long long R = static_cast<long long>(rd) * rh * rw;
+    // 32-bit shared-window addresses of this thread's ring slots
+    const unsigned ring_s = static_cast<unsigned>(__cvta_generic_to_shared(ring));
+    const unsigned ring_w = ring_s + tid * 16;                                 // + stage * kWStage
+    const unsigned ring_l = ring_s + S * kAccThreads * 16 + tid * IB;          // + stage * kLStage + k * kLSlot
+    constexpr unsigned kWStage = kAccThreads * 16, kLSlot = kAccThreads * IB, kLStage = KC * kLSlot;
+    const unsigned R_bytes = static_cast<unsigned>(R) * static_cast<unsigned>(sizeof(LT));
+
+    // ---- tile -----------------------------------------------------------------------------------
+    const int wt = blockIdx.x % p.n_wtiles, ht = blockIdx.x / p.n_wtiles;
+    const int ld = p.box_lo[0] + blockIdx.y;
+    const int b = p.b_lo + blockIdx.z;
+    const int lh0 = p.box_lo[1] + ht * p.th;
+    const int rows = min(p.th, p.box_lo[1] + p.box_n[1] - lh0);
+    const int q0 = wt * p.tq;
+    const int nqt = min(p.tq, p.nq - q0);
+    const int lw0 = p.box_lo[2] + q0 * 4;
+    const int gd = ld + g.org[0], gh0 = lh0 + g.org[1], gw0 = lw0 + g.org[2];
+    const int gw_last = min(gw0 + nqt * 4, g.org[2] + g.ext[2]) - 1;  // last real voxel of the tile row
 
     // this volume's slice of the call's window range
     const long long vol0 = static_cast<long long>(b) * g.n_local;
     const long long n0 = p.g0 > vol0 ? p.g0 - vol0 : 0;
     const long long n1 = (p.g1 - vol0) < g.n_local ? (p.g1 - vol0) : g.n_local;
 
-    // cover ranges (global window indices per axis), W per element
-    const int cvd = g.cover[0][gd], cvh = g.cover[1][gh];
-    const int dlo = cvd & 0xffff, dhi = cvd >> 16, hlo = cvh & 0xffff, hhi = cvh >> 16;
-    bool valid[4];
-    int wlo = 0x7fffffff, whi = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        valid[e] = lw + e < g.ext[2];
-        if (valid[e]) {
-            const int c = g.cover[2][gw + e];
-            wlo = min(wlo, c & 0xffff);
-            whi = max(whi, c >> 16);
-        }
-    }
-    if (!valid[0]) return;
-    // clipped to the windows this buffer owns
-    const int odlo = max(dlo, g.wlo[0]), odhi = min(dhi, g.whi[0]);
-    const int ohlo = max(hlo, g.wlo[1]), ohhi = min(hhi, g.whi[1]);
-    const int owlo = max(wlo, g.wlo[2]), owhi = min(whi, g.whi[2]);
+    // windows (global index ranges per axis) that can touch the tile, clipped to the ones this buffer owns
+    const int cvd = g.cover[0][gd];
+    const int dlo = max(cvd & 0xffff, g.wlo[0]), dhi = min(cvd >> 16, g.whi[0]);
+    const int hlo = max(g.cover[1][gh0] & 0xffff, g.wlo[1]), hhi = min(g.cover[1][gh0 + rows - 1] >> 16, g.whi[1]);
+    const int wlo = max(g.cover[2][gw0] & 0xffff, g.wlo[2]), whi = min(g.cover[2][gw_last] >> 16, g.whi[2]);
+    const int nh = hhi - hlo, nw = whi - wlo;
+    const int ncand = (dhi - dlo) * nh * nw;
+    if (ncand <= 0) return;
+    const int nchunks = (ncand + kMaxCand - 1) / kMaxCand;
 
-    // pass 1 (integers only): which elements were touched before / are touched now / will be touched later
-    unsigned before = 0, now = 0, after = 0;
-    for (int id = odlo; id < odhi; ++id)
-        for (int ih = ohlo; ih < ohhi; ++ih)
-            for (int iw = owlo; iw < owhi; ++iw) {
-                const long long n =
-                    (static_cast<long long>(id - g.wlo[0]) * g.nwl[1] + (ih - g.wlo[1])) * g.nwl[2] + (iw - g.wlo[2]);
-                const int ww = gw - g.starts[2][iw];
-                unsigned m = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (valid[e] && ww + e >= 0 && ww + e < rw) m |= 1u << e;
-                if (n < n0) before |= m;
-                else if (n >= n1) after |= m;
-                else now |= m;
+    auto build_chunk = [&](int c0) {
+        const int c = c0 + tid;
+        if (tid < kMaxCand && c < ncand) {
+            const int iw = wlo + c % nw;
+            const int ih = hlo + (c / nw) % nh;
+            const int id = dlo + c / (nw * nh);
+            const long long n =
+                (static_cast<long long>(id - g.wlo[0]) * g.nwl[1] + (ih - g.wlo[1])) * g.nwl[2] + (iw - g.wlo[2]);
+            const int cls = n < n0 ? kBefore : (n >= n1 ? kAfter : kNow);
+            const int sd = g.starts[0][id], sh = g.starts[1][ih], sw = g.starts[2][iw];
+            const int wofs = ((gd - sd) * rh - sh) * rw - sw;
+            s_sh[tid] = sh;
+            s_sw[tid] = sw;
+            s_cls[tid] = cls;
+            s_wofs[tid] = wofs;
+            const LT* ptr = nullptr;
+            if (cls == kNow) {
+                const long long gi = vol0 + n - p.g0;  // position inside this call's window range
+                const long long bi = gi / p.sw_batch;
+                const long long bj = gi - bi * p.sw_batch;
+                ptr = static_cast<const LT*>(p.batch[bi]) + bj * g.K * R + wofs;
+                s_any_now = 1;
             }
-    if (now == 0) return;
+            s_ptr[tid] = ptr;
+        }
+    };
+
+    // ---- this thread's quad ------------------------------------------------------------------------
+    const int r = tid / p.tq, qi = tid - r * p.tq;
+    const bool active = r < rows && qi < nqt;
+    const int lh = lh0 + r, lw = lw0 + qi * 4;
+    const int gh = gh0 + r, gw = gw0 + qi * 4;
+    const int hw = gh * rw + gw;
+    unsigned vmask = 0;  // elements of the quad that are real voxels
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (active && lw + e < g.ext[2]) vmask |= 1u << e;
+
+    // element mask of window (sh, sw) over this quad
+    auto cover_mask = [&](int sh, int sw) -> unsigned {
+        if (static_cast<unsigned>(gh - sh) >= static_cast<unsigned>(rh)) return 0u;
+        const int ww = gw - sw;
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (static_cast<unsigned>(ww + e) < static_cast<unsigned>(rw)) m |= 1u << e;
+        return m & vmask;
+    };
+
+    // ---- phase 1: who touched / touches / will touch each element; which listed windows feed this quad ------
+    // fast: the window of this launch covers the whole quad 16-byte aligned -> ring pipeline; slow: partial cover
+    if (tid == 0) s_any_now = 0;
+    unsigned before = 0, now = 0, after = 0;
+    unsigned long long fast = 0ull, slow = 0ull;
+    auto scan_chunk = [&](int cn, bool flags) {
+        fast = 0ull;
+        slow = 0ull;
+        for (int c = 0; c < cn; ++c) {
+            const int sw = s_sw[c];
+            const unsigned m = cover_mask(s_sh[c], sw);
+            const int cls = s_cls[c];
+            if (flags) {
+                before |= cls == kBefore ? m : 0u;
+                after |= cls == kAfter ? m : 0u;
+                now |= cls == kNow ? m : 0u;
+            }
+            if (cls == kNow && m != 0u) {
+                if (m == 0xFu && p.vec_ok && (((gw - sw) & 3) == 0)) fast |= 1ull << c;
+                else slow |= 1ull << c;
+            }
+        }
+    };
+    for (int ch = 0; ch < nchunks; ++ch) {
+        __syncthreads();
+        build_chunk(ch * kMaxCand);
+        __syncthreads();
+        scan_chunk(min(kMaxCand, ncand - ch * kMaxCand), true);
+    }
+    if (s_any_now == 0) return;  // uniform: nothing of this launch lands in the tile
     const unsigned complete = p.fuse != MSS_FUSE_NONE ? (now & ~after) : 0u;
 
-    // window-weight count of finished voxels: ascending fp32 sum over ALL covering windows of the grid
-    // (engine/utils.py:148 accumulates the same weights in the same order into count_map)
-    float cnt[4] = {0.f, 0.f, 0.f, 0.f};
-    if (complete) {
-        for (int id = dlo; id < dhi; ++id)
-            for (int ih = hlo; ih < hhi; ++ih) {
-                const float* row = p.imp + (static_cast<long long>(gd - g.starts[0][id]) * rh + (gh - g.starts[1][ih])) * rw;
-                for (int iw = wlo; iw < whi; ++iw) {
-                    const int ww = gw - g.starts[2][iw];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (valid[e] && ww + e >= 0 && ww + e < rw) cnt[e] = __fadd_rn(cnt[e], __ldg(row + ww + e));
-                }
-            }
-    }
-
     const long long plane = static_cast<long long>(g.ext[1]) * g.pitch;
-    const long long vox = static_cast<long long>(ld) * plane + static_cast<long long>(lh) * g.pitch + lw;
-    float* accb = p.acc != nullptr ? p.acc + static_cast<long long>(b) * g.K * g.ext[0] * plane + vox : nullptr;
     const long long cstride = static_cast<long long>(g.ext[0]) * plane;
+    float* accb = p.acc != nullptr ? p.acc + static_cast<long long>(b) * g.K * cstride + static_cast<long long>(ld) * plane +
+                                         static_cast<long long>(lh) * g.pitch + lw
+                                   : nullptr;
+
+    // window-weight count of the voxels finished here: ascending fp32 sum over ALL covering windows, i.e. what
+    // engine/utils.py:148 accumulates into count_map.  Weights only (L1/L2-resident map), logits mode only.
+    float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.fuse == MSS_FUSE_LOGITS) {
+        for (int ch = 0; ch < nchunks; ++ch) {
+            if (nchunks > 1) {
+                __syncthreads();
+                build_chunk(ch * kMaxCand);
+                __syncthreads();
+            }
+            const int cn = min(kMaxCand, ncand - ch * kMaxCand);
+            if (complete == 0u) continue;
+            for (int c = 0; c < cn; ++c) {
+                const unsigned m = cover_mask(s_sh[c], s_sw[c]);
+                if (m == 0u) continue;
+                const float* wp = p.imp + (s_wofs[c] + hw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (m & (1u << e)) cnt[e] = __fadd_rn(cnt[e], __ldg(wp + e));
+            }
+        }
+    }
 
     ArgmaxState am[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) am[e].reset();
 
-    for (int k0 = 0; k0 < g.K; k0 += kAccTK) {
-        float4 a[kAccTK];
+    // ---- phase 2: KC classes at a time, S windows in flight per thread -------------------------------------------
+    for (int k0 = 0; k0 < g.K; k0 += KC) {
+        const int kc = min(KC, g.K - k0);
+        float4 a[KC];
 #pragma unroll
-        for (int k = 0; k < kAccTK; ++k) {
+        for (int k = 0; k < KC; ++k) {
             a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (before && k0 + k < g.K) {
+            if (now != 0u && before != 0u && k < kc) {
                 const float4 v = *reinterpret_cast<const float4*>(accb + (k0 + k) * cstride);
                 a[k].x = (before & 1u) ? v.x : 0.f;
                 a[k].y = (before & 2u) ? v.y : 0.f;
@@ -164,81 +314,115 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const __grid_co
                 a[k].w = (before & 8u) ? v.w : 0.f;
             }
         }
-        for (int id = odlo; id < odhi; ++id)
-            for (int ih = ohlo; ih < ohhi; ++ih)
-                for (int iw = owlo; iw < owhi; ++iw) {
-                    const long long n =
-                        (static_cast<long long>(id - g.wlo[0]) * g.nwl[1] + (ih - g.wlo[1])) * g.nwl[2] + (iw - g.wlo[2]);
-                    if (n < n0 || n >= n1) continue;
-                    const int ww = gw - g.starts[2][iw];
-                    if (ww <= -4 || ww >= rw) continue;
-                    const long long gi = vol0 + n - p.g0;  // position inside this call's window range
-                    const int bi = static_cast<int>(gi / p.sw_batch);
-                    const int bj = static_cast<int>(gi - static_cast<long long>(bi) * p.sw_batch);
-                    const long long off = (static_cast<long long>(gd - g.starts[0][id]) * rh + (gh - g.starts[1][ih])) * rw + ww;
-                    const LT* lg = static_cast<const LT*>(p.batch[bi]) + static_cast<long long>(bj) * g.K * R + off;
-                    const float* wp = p.imp + off;
-                    if (p.vec_ok && ww >= 0 && ww + 3 < rw && (ww & 3) == 0 && valid[3]) {
-                        const float4 w4 = ldg_f4(wp);
-                        float4 l[kAccTK];
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int cn = min(kMaxCand, ncand - ch * kMaxCand);
+            if (nchunks > 1) {  // the single-chunk list and masks of phase 1 are still in place otherwise
+                __syncthreads();
+                build_chunk(ch * kMaxCand);
+                __syncthreads();
+                scan_chunk(cn, false);
+            }
+            if ((fast | slow) == 0ull) continue;
+
+            // full: all KC classes of this pass exist (no predicates in the unrolled loops)
+            auto run = [&](auto full_tag) {
+                constexpr bool kFull = decltype(full_tag)::value;
+                auto issue = [&](int c, int st) {  // start fetching window c of the list into ring stage st
+                    if (c < cn && ((fast >> c) & 1ull)) {
+                        cp_async16(ring_w + st * kWStage, p.imp + (s_wofs[c] + hw));
+                        const char* lg = reinterpret_cast<const char*>(s_ptr[c] + hw) + static_cast<size_t>(k0) * R_bytes;
+                        const unsigned dst = ring_l + st * kLStage;
 #pragma unroll
-                        for (int k = 0; k < kAccTK; ++k)
-                            if (k0 + k < g.K) l[k] = LogitLoad<LT>::quad(lg + (k0 + k) * R);
+                        for (int k = 0; k < KC; ++k)
+                            if (kFull || k < kc) Slot<LT>::fetch(dst + k * kLSlot, lg + static_cast<unsigned>(k) * R_bytes);
+                    }
+                    cp_async_commit();
+                };
+                int st_issue = 0;
 #pragma unroll
-                        for (int k = 0; k < kAccTK; ++k)
-                            if (k0 + k < g.K) {
-                                a[k].x = __fadd_rn(a[k].x, __fmul_rn(w4.x, l[k].x));
-                                a[k].y = __fadd_rn(a[k].y, __fmul_rn(w4.y, l[k].y));
-                                a[k].z = __fadd_rn(a[k].z, __fmul_rn(w4.z, l[k].z));
-                                a[k].w = __fadd_rn(a[k].w, __fmul_rn(w4.w, l[k].w));
+                for (int c = 0; c < S - 1; ++c) {
+                    issue(c, st_issue);
+                    st_issue = st_issue + 1 == S ? 0 : st_issue + 1;
+                }
+                int st_cons = 0;
+                for (int c = 0; c < cn; ++c) {
+                    issue(c + S - 1, st_issue);
+                    st_issue = st_issue + 1 == S ? 0 : st_issue + 1;
+                    cp_async_wait<S - 1>();  // everything up to window c has landed
+                    if ((fast >> c) & 1ull) {
+                        const float4 w4 = lds_f4(ring_w + st_cons * kWStage);
+                        const unsigned src = ring_l + st_cons * kLStage;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k)
+                            if (kFull || k < kc) {
+                                const float4 l = Slot<LT>::read(src + k * kLSlot);
+                                a[k].x = __fadd_rn(a[k].x, __fmul_rn(w4.x, l.x));
+                                a[k].y = __fadd_rn(a[k].y, __fmul_rn(w4.y, l.y));
+                                a[k].z = __fadd_rn(a[k].z, __fmul_rn(w4.z, l.z));
+                                a[k].w = __fadd_rn(a[k].w, __fmul_rn(w4.w, l.w));
                             }
-                    } else {
+                    } else if ((slow >> c) & 1ull) {
+                        const unsigned m = cover_mask(s_sh[c], s_sw[c]);
+                        const float* wp = p.imp + (s_wofs[c] + hw);
+                        const LT* lg = s_ptr[c] + hw + static_cast<long long>(k0) * R;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            if (!(valid[e] && ww + e >= 0 && ww + e < rw)) continue;
+                            if (!(m & (1u << e))) continue;
                             const float w1 = __ldg(wp + e);
 #pragma unroll
-                            for (int k = 0; k < kAccTK; ++k)
-                                if (k0 + k < g.K) {
+                            for (int k = 0; k < KC; ++k)
+                                if (kFull || k < kc) {
                                     float& dst = comp(a[k], e);
-                                    dst = __fadd_rn(dst, __fmul_rn(w1, LogitLoad<LT>::one(lg + (k0 + k) * R + e)));
+                                    dst = __fadd_rn(dst, __fmul_rn(w1, LogitLoad<LT>::one(lg + k * R + e)));
                                 }
                         }
                     }
+                    st_cons = st_cons + 1 == S ? 0 : st_cons + 1;
                 }
-        if (complete) {
+            };
+            if (kc == KC) run(std::true_type{});
+            else run(std::false_type{});
+            cp_async_wait<0>();
+        }
+        if (now == 0u) continue;
+        if (p.fuse == MSS_FUSE_LOGITS && complete) {
 #pragma unroll
-            for (int k = 0; k < kAccTK; ++k)
-                if (k0 + k < g.K) {
+            for (int k = 0; k < KC; ++k)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (complete & (1u << e)) {
-                            float& v = comp(a[k], e);
-                            v = __fdiv_rn(v, cnt[e]);  // engine/utils.py:151
-                            if (p.fuse == MSS_FUSE_LABELS) am[e].push(v, k0 + k);
-                        }
+                for (int e = 0; e < 4; ++e)
+                    if (complete & (1u << e)) {
+                        float& v = comp(a[k], e);
+                        v = __fdiv_rn(v, cnt[e]);  // engine/utils.py:151
+                    }
+        }
+        if (p.fuse == MSS_FUSE_LABELS && complete) {
+            // argmax of the raw weighted sums: dividing every class by the same positive count cannot reorder them
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                if (k < kc) {
+                    am[0].push(a[k].x, k0 + k);
+                    am[1].push(a[k].y, k0 + k);
+                    am[2].push(a[k].z, k0 + k);
+                    am[3].push(a[k].w, k0 + k);
                 }
         }
         // store: skipped only when the whole quad was finished into labels
-        const unsigned live = (valid[0] ? 1u : 0u) | (valid[1] ? 2u : 0u) | (valid[2] ? 4u : 0u) | (valid[3] ? 8u : 0u);
-        const bool all_to_labels = p.fuse == MSS_FUSE_LABELS && (complete & live) == live;
+        const bool all_to_labels = p.fuse == MSS_FUSE_LABELS && (complete & vmask) == vmask;
         if (accb != nullptr && !all_to_labels) {
 #pragma unroll
-            for (int k = 0; k < kAccTK; ++k)
-                if (k0 + k < g.K) *reinterpret_cast<float4*>(accb + (k0 + k) * cstride) = a[k];
+            for (int k = 0; k < KC; ++k)
+                if (k < kc) *reinterpret_cast<float4*>(accb + (k0 + k) * cstride) = a[k];
         }
     }
 
     if (p.fuse == MSS_FUSE_LABELS && complete) {
         uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
                        static_cast<long long>(lh) * p.label_pitch + lw;
-        unsigned ties = 0;
-        unsigned packed = 0;
+        unsigned ties = 0, packed = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (complete & (1u << e)) {
-                const int lbl = am[e].label();
-                packed |= static_cast<unsigned>(lbl) << (8 * e);
+                packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
                 ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
             }
         if (complete == 0xFu && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
@@ -283,6 +467,37 @@ static void window_range_box(const mss_layout_t* lay, long long n0, long long n1
     }
 }
 
+template <typename LT, int KC, int S, int MINB>
+static cudaError_t launch_one(dim3 grid, cudaStream_t s, const AccParams& p) {
+    constexpr size_t smem = acc_smem_bytes<LT, KC, S>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(accumulate_kernel<LT, KC, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    accumulate_kernel<LT, KC, S, MINB><<<grid, kAccThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename LT>
+static cudaError_t launch_for_k(int K, dim3 grid, cudaStream_t s, const AccParams& p) {
+    // classes per register pass (KC): exact divisors avoid predication, 8 with a predicated tail otherwise.
+    // Ring depth S and the 4-CTA/SM register cap were picked on B200 with benchmarks/kernel_bench.py: 16 resident
+    // warps/SM matter more than a deeper ring (K=14: KC=7,S=3 -> 5.6 TB/s; KC=14,S=3 -> 4.4 TB/s; KC=7,S=6 -> 2.8 TB/s).
+    static const int variant = getenv("MSS_ACC_VARIANT") ? atoi(getenv("MSS_ACC_VARIANT")) : 0;  // tuning knob
+    if (K % 14 == 0 && variant == 2) return launch_one<LT, 14, 3, 2>(grid, s, p);
+    if (K % 7 == 0 && variant == 1) return launch_one<LT, 7, 4, 4>(grid, s, p);
+    if (K % 7 == 0) return launch_one<LT, 7, 3, 4>(grid, s, p);
+    if (K % 8 == 0) return launch_one<LT, 8, 3, 4>(grid, s, p);
+    if (K % 5 == 0) return launch_one<LT, 5, 4, 4>(grid, s, p);
+    if (K % 4 == 0) return launch_one<LT, 4, 4, 4>(grid, s, p);
+    if (K % 3 == 0) return launch_one<LT, 3, 6, 4>(grid, s, p);
+    if (K == 2) return launch_one<LT, 2, 8, 4>(grid, s, p);
+    return launch_one<LT, 8, 3, 4>(grid, s, p);
+}
+
 }  // namespace mss
 
 using namespace mss;
@@ -310,35 +525,33 @@ extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_
     MSS_REQUIRE(fuse == MSS_FUSE_NONE || fuse == MSS_FUSE_LOGITS || fuse == MSS_FUSE_LABELS, MSS_E_ARG,
                 "accumulate: unknown fuse mode %d", fuse);
     MSS_REQUIRE(g.pitch % 4 == 0, MSS_E_ALIGN, "accumulate: pitch_w (%d) must be a multiple of 4", g.pitch);
+    MSS_REQUIRE(static_cast<long long>(g.img[1]) * g.roi[2] + g.img[2] < (1LL << 31) &&
+                    static_cast<long long>(g.roi[0]) * g.roi[1] * g.roi[2] < (1LL << 30),
+                MSS_E_UNSUPPORTED, "accumulate: roi / image too large for 32-bit window offsets");
     const bool covers_all = first_window == 0 && n_windows == total;
+    if (fuse != MSS_FUSE_NONE)
+        for (int a = 0; a < 3; ++a)
+            MSS_REQUIRE(g.wlo[a] == 0 && g.whi[a] == g.ns[a], MSS_E_ARG,
+                        "accumulate: fused finishing needs a buffer that owns every window (axis %d)", a);
     if (fuse == MSS_FUSE_LABELS) {
         MSS_REQUIRE(labels != nullptr && label_pitch_w >= g.ext[2], MSS_E_ARG, "accumulate: labels buffer / pitch invalid");
         MSS_REQUIRE(g.K <= 255, MSS_E_UNSUPPORTED, "accumulate: uint8 labels need K <= 255");
         MSS_REQUIRE(acc != nullptr || covers_all, MSS_E_ARG,
                     "accumulate: acc may be NULL only when one call covers every owned window");
-        for (int a = 0; a < 3; ++a)
-            MSS_REQUIRE(g.wlo[a] == 0 && g.whi[a] == g.ns[a], MSS_E_ARG,
-                        "accumulate: fused finishing needs a buffer that owns every window (axis %d)", a);
     } else {
         MSS_REQUIRE(acc != nullptr, MSS_E_ARG, "accumulate: acc is null");
-        if (fuse == MSS_FUSE_LOGITS)
-            for (int a = 0; a < 3; ++a)
-                MSS_REQUIRE(g.wlo[a] == 0 && g.whi[a] == g.ns[a], MSS_E_ARG,
-                            "accumulate: fused finishing needs a buffer that owns every window (axis %d)", a);
     }
     MSS_REQUIRE(acc == nullptr || reinterpret_cast<uintptr_t>(acc) % 16 == 0, MSS_E_ALIGN,
                 "accumulate: acc must be 16-byte aligned");
     MSS_REQUIRE(logits_dtype == MSS_F32 || logits_dtype == MSS_F16 || logits_dtype == MSS_BF16, MSS_E_ARG,
                 "accumulate: unknown logits dtype %d", logits_dtype);
     const int esz = logits_dtype == MSS_F32 ? 4 : 2;
-    const long long R = static_cast<long long>(g.roi[0]) * g.roi[1] * g.roi[2];
     int vec_ok = (g.roi[2] % 4 == 0) && (reinterpret_cast<uintptr_t>(importance_map) % 16 == 0);
     for (int i = 0; i < n_batches; ++i) {
         MSS_REQUIRE(batch_ptrs[i] != nullptr, MSS_E_ARG, "accumulate: batch pointer %d is null", i);
         p.batch[i] = batch_ptrs[i];
         if (reinterpret_cast<uintptr_t>(batch_ptrs[i]) % (4 * esz) != 0) vec_ok = 0;
     }
-    (void)R;
     p.sw_batch = sw_batch;
     p.g0 = first_window;
     p.g1 = first_window + n_windows;
@@ -372,18 +585,23 @@ extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_
         p.box_n[a] = hi[a] - lo[a];
     }
     p.nq = (p.box_n[2] + 3) / 4;
+    // tile: up to 32 quads (128 voxels) along W, split evenly; as many rows as fit 128 threads
+    p.n_wtiles = (p.nq + 31) / 32;
+    p.tq = (p.nq + p.n_wtiles - 1) / p.n_wtiles;
+    p.th = kAccThreads / p.tq;
     p.b_lo = b_lo;
-    const long long per_plane = static_cast<long long>(p.nq) * p.box_n[1];
-    dim3 grid(static_cast<unsigned>((per_plane + kAccThreads - 1) / kAccThreads), static_cast<unsigned>(p.box_n[0]),
+    const int n_htiles = (p.box_n[1] + p.th - 1) / p.th;
+    dim3 grid(static_cast<unsigned>(p.n_wtiles * n_htiles), static_cast<unsigned>(p.box_n[0]),
               static_cast<unsigned>(b_hi - b_lo + 1));
     MSS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MSS_E_UNSUPPORTED, "accumulate: box too large for one launch");
     cudaStream_t s = as_stream(stream);
+    cudaError_t e;
     if (logits_dtype == MSS_F32)
-        accumulate_kernel<float><<<grid, kAccThreads, 0, s>>>(p);
+        e = launch_for_k<float>(g.K, grid, s, p);
     else if (logits_dtype == MSS_F16)
-        accumulate_kernel<__half><<<grid, kAccThreads, 0, s>>>(p);
+        e = launch_for_k<__half>(g.K, grid, s, p);
     else
-        accumulate_kernel<__nv_bfloat16><<<grid, kAccThreads, 0, s>>>(p);
-    MSS_CUDA(cudaGetLastError());
+        e = launch_for_k<__nv_bfloat16>(g.K, grid, s, p);
+    MSS_CUDA(e);
     return MSS_OK;
 }
