@@ -438,7 +438,7 @@ def sliding_window_infer(
 
 def labels_from_logits(acc: torch.Tensor, st: Stitcher, *, tie_tol: float = 1e-5, normalise: bool = False,
                        box: Optional[Tuple[Sequence[int], Sequence[int]]] = None,
-                       labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       labels: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``mss_finalize_labels`` on a stitcher's accumulator: [normalise +] argmax -> uint8 (engine/test.py:140-141)."""
     plan = st.plan
     ext = plan.extent
@@ -448,7 +448,8 @@ def labels_from_logits(acc: torch.Tensor, st: Stitcher, *, tie_tol: float = 1e-5
     stream = torch.cuda.current_stream().cuda_stream
     with st.timer("finalize"):
         rc = st.lib.mss_finalize_labels(C.byref(st.lay), acc.data_ptr(), st.imp.data_ptr(), 1 if normalise else 0,
-                                        _lib.I3(*lo), _lib.I3(*hi), labels.data_ptr(), ext[2], None, None, float(tie_tol),
+                                        _lib.I3(*lo), _lib.I3(*hi), labels.data_ptr(), ext[2],
+                                        None if logits_out is None else logits_out.data_ptr(), None, float(tie_tol),
                                         st.near.data_ptr(), stream)
     _lib.check(rc, "mss_finalize_labels")
     if st.stats is not None:
