@@ -151,9 +151,11 @@ def exchange_halos(acc: torch.Tensor, part: SlabPartition, rank: int, group: Any
 def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: WindowGrid, part: SlabPartition,
                rank: int, mode: Any = "gaussian", *, sw_batch_size: int = 4, sigma_scale: Any = 0.125, cval: float = 0.0,
                affine: Optional[torch.Tensor] = None, tuple_input: bool = False, tie_tol: float = 1e-5,
-               stats: Any = None, time_kernels: bool = False, group_bytes: Optional[int] = None):
+               stats: Any = None, time_kernels: bool = False, group_bytes: Optional[int] = None,
+               volume_is_slab: bool = False):
     """Everything rank `rank` does before the exchange: slab copy, extract -> backbone -> accumulate of its own
-    windows into raw weighted sums over its buffer box.  Returns the Stitcher (``.acc`` is the buffer)."""
+    windows into raw weighted sums over its buffer box.  Returns the Stitcher (``.acc`` is the buffer).
+    ``volume`` is the full volume, or only this rank's slab ``[buf_lo, buf_hi)`` when ``volume_is_slab``."""
     from .importance import importance_map as build_imp
     from .inferer import StitchPlan, Stitcher
 
@@ -166,7 +168,10 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
     win_lo, win_hi = [0, 0, 0], list(grid.n_starts)
     win_lo[ax], win_hi[ax] = part.win_lo[rank], part.win_hi[rank]
     plan = StitchPlan(grid, dev, nb, win_lo, win_hi, origin, extent)
-    slab = _region(volume, ax, origin[ax], origin[ax] + extent[ax]).to(device=dev, dtype=torch.float32).contiguous()
+    src = volume if volume_is_slab else _region(volume, ax, origin[ax], origin[ax] + extent[ax])
+    if tuple(src.shape[2:]) != tuple(extent):
+        raise ValueError(f"slab has spatial shape {tuple(src.shape[2:])}, expected {tuple(extent)}")
+    slab = src.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
     imp = build_imp(grid.roi, mode, sigma_scale, dev)
     st = Stitcher(plan, imp, fuse=_lib.FUSE_NONE, sw_batch=sw_batch_size, tie_tol=tie_tol, group_bytes=group_bytes,
                   stats=stats, time_kernels=time_kernels)
