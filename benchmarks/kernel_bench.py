@@ -27,6 +27,7 @@ SHAPES = {
     "btcv": dict(shape=(1, 1, 512, 512, 200), k=14, m=5),
     "brats": dict(shape=(1, 4, 240, 240, 155), k=3, m=5),
     "small": dict(shape=(1, 1, 192, 192, 200), k=14, m=5),
+    "wholebody": dict(shape=(1, 1, 512, 512, 1024), k=14, m=5),  # label-map kernels only (--only vote,dice)
 }
 
 
@@ -94,7 +95,7 @@ def main():
     imp = importance_map((96, 96, 96), "gaussian", 0.125, dev)
     n_win = plan.grid.n_windows
     B = args.sw_batch
-    vol = torch.randn(cfg["shape"], device=dev)
+    vol = inferer._tma_ready(torch.randn(cfg["shape"], device=dev), plan.grid, 0.0)  # as the inferer hands it to extract
 
     if want("importance"):
         def f():
@@ -109,13 +110,13 @@ def main():
             st.use_tma = tma
             med, mn = timed(lambda: st.extract(vol, 0, B, 0.0), args.reps, flush)
             report(f"extract B={B} tma={int(tma)}", 8 * B * cin * r, med, mn, "one predictor batch")
-        big = 40
-        st.use_tma = True
-        med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
-        report(f"extract B={big} tma=1", 8 * big * cin * r, med, mn)
-        st.use_tma = False
-        med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
-        report(f"extract B={big} tma=0", 8 * big * cin * r, med, mn)
+        for big in (40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))):
+            st.use_tma = True
+            med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
+            report(f"extract B={big} tma=1", 8 * big * cin * r, med, mn, "extract-ahead group" if big > 40 else "")
+            st.use_tma = False
+            med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
+            report(f"extract B={big} tma=0", 8 * big * cin * r, med, mn)
 
     if want("accumulate") or want("accumulate_rmw") or want("finalize"):
         n_batches = -(-n_win // B)

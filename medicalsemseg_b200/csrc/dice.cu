@@ -3,33 +3,23 @@
 //
 // TP[c] = #(pred==c & label==c), P[c] = #(pred==c), Y[c] = #(label==c) as exact int64 - the reference
 // sums fp32 one-hots, which stops being exact above 2^24 voxels per class; Dice is derived from the
-// integers on the host in float64.  Each thread streams 16 voxels per step and counts into packed
-// 8-bit fields held in 64-bit registers (K <= 16: two registers per quantity), spilling to a
-// shared-memory histogram every 240 voxels and to global int64 atomics once per block.
+// integers on the host in float64.
+//
+// The kernel has 2 bytes of traffic per voxel, i.e. ~11 instructions per voxel at the HBM roofline, so
+// the labels are counted bit-sliced: a thread turns 32 voxels (2 x 16-byte loads per map) into four
+// 32-bit bit planes (nibble pack + a 4x4 bit-matrix transpose: ~24 instructions), after which the
+// indicator of class c over all 32 voxels is one LOP3 and its count one POPC.  Per-thread counts live in
+// registers as 16-bit pairs; a warp reduces them with REDUX and adds them to a shared histogram, one
+// int64 atomic per class and block reaches global memory.  Labels >= 16 (legal: they belong to no class)
+// send their 32-voxel chunk down a scalar path.
 #include "common.cuh"
+#include "bitslice.cuh"
 
 namespace mss {
 
 constexpr int kDiceThreads = 256;
-
-// add one to byte field (c & 7) of lo (c < 8) or hi (c >= 8); c >= 16 adds nothing
-__device__ __forceinline__ void bump(unsigned long long& lo, unsigned long long& hi, unsigned c) {
-    const unsigned long long one = 1ull << (8 * (c & 7u));
-    lo += (c < 8u) ? one : 0ull;
-    hi += (c >= 8u && c < 16u) ? one : 0ull;
-}
-
-__device__ __forceinline__ void spill(unsigned long long& lo, unsigned long long& hi, unsigned* sh) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const unsigned a = static_cast<unsigned>(lo >> (8 * c)) & 0xffu;
-        const unsigned b = static_cast<unsigned>(hi >> (8 * c)) & 0xffu;
-        if (a) atomicAdd(&sh[c], a);
-        if (b) atomicAdd(&sh[8 + c], b);
-    }
-    lo = 0ull;
-    hi = 0ull;
-}
+constexpr int kDiceChunk = 32;           // voxels per thread and iteration
+constexpr int kDiceFlushIters = 63;      // 16-bit halves survive the packed warp sum: 63 * 32 voxels * 32 lanes < 65536
 
 template <typename LabelT>
 __device__ __forceinline__ unsigned label_class(LabelT v);
@@ -39,73 +29,133 @@ template <>
 __device__ __forceinline__ unsigned label_class<float>(float v) {
     // integer-valued float labels (engine/test.py:40); anything else belongs to no class
     const int i = __float2int_rz(v);
-    return (static_cast<float>(i) == v && i >= 0) ? static_cast<unsigned>(i) : 0xffu;
+    return (static_cast<float>(i) == v && i >= 0 && i < 255) ? static_cast<unsigned>(i) : 0xffu;
 }
 
+__device__ __forceinline__ unsigned pack4(float4 f) {
+    return label_class<float>(f.x) | (label_class<float>(f.y) << 8) | (label_class<float>(f.z) << 16) |
+           (label_class<float>(f.w) << 24);
+}
+
+// raw 16-byte loads of one 32-voxel chunk (kept as loaded so the next chunk can be in flight during the math)
 template <typename LabelT>
+struct ChunkRegs;
+template <>
+struct ChunkRegs<uint8_t> {
+    uint4 p0, p1, y0, y1;
+    __device__ __forceinline__ void load(const uint8_t* pred, const uint8_t* label, long long i) {
+        p0 = ld_stream_u4(pred + i * kDiceChunk), p1 = ld_stream_u4(pred + i * kDiceChunk + 16);
+        y0 = ld_stream_u4(label + i * kDiceChunk), y1 = ld_stream_u4(label + i * kDiceChunk + 16);
+    }
+    __device__ __forceinline__ void label_words(unsigned (&yw)[8]) const {
+        yw[0] = y0.x, yw[1] = y0.y, yw[2] = y0.z, yw[3] = y0.w, yw[4] = y1.x, yw[5] = y1.y, yw[6] = y1.z, yw[7] = y1.w;
+    }
+};
+template <>
+struct ChunkRegs<float> {
+    uint4 p0, p1;
+    float4 f[8];
+    __device__ __forceinline__ void load(const uint8_t* pred, const float* label, long long i) {
+        p0 = ld_stream_u4(pred + i * kDiceChunk), p1 = ld_stream_u4(pred + i * kDiceChunk + 16);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) f[w] = ld_stream_f4(label + i * kDiceChunk + 4 * w);
+    }
+    __device__ __forceinline__ void label_words(unsigned (&yw)[8]) const {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) yw[w] = pack4(f[w]);
+    }
+};
+
+// KP = ceil(K / 2) class pairs
+template <typename LabelT, int KP>
 __global__ void __launch_bounds__(kDiceThreads) dice_kernel(const uint8_t* __restrict__ pred, const LabelT* __restrict__ label,
                                                             long long n, int K, long long* __restrict__ counts, int vec_ok) {
-    __shared__ unsigned sh[3][16];
+    __shared__ unsigned sh[3][16];  // TP, P, Y
     if (threadIdx.x < 48) (&sh[0][0])[threadIdx.x] = 0u;
     __syncthreads();
-    unsigned long long tp_lo = 0, tp_hi = 0, p_lo = 0, p_hi = 0, y_lo = 0, y_hi = 0;
-    int pending = 0;
     const unsigned Ku = static_cast<unsigned>(K);
-    auto one = [&](unsigned pc, unsigned yc) {
-        pc = pc < Ku ? pc : 0xffu;
-        yc = yc < Ku ? yc : 0xffu;
-        bump(p_lo, p_hi, pc);
-        bump(y_lo, y_hi, yc);
-        bump(tp_lo, tp_hi, pc == yc ? pc : 0xffu);
+    auto slow_one = [&](unsigned pc, unsigned yc) {
+        if (pc < Ku) atomicAdd(&sh[1][pc], 1u);
+        if (yc < Ku) atomicAdd(&sh[2][yc], 1u);
+        if (pc == yc && pc < Ku) atomicAdd(&sh[0][pc], 1u);
     };
+
+    unsigned tp[8], pp[8], yy[8];  // classes (2i, 2i+1) as 16-bit halves
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tp[i] = pp[i] = yy[i] = 0u;
+    auto flush = [&]() {  // warp sums of the packed counters (REDUX), one shared atomic per class and warp
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            const unsigned a = __reduce_add_sync(0xffffffffu, tp[i]);
+            const unsigned b = __reduce_add_sync(0xffffffffu, pp[i]);
+            const unsigned c = __reduce_add_sync(0xffffffffu, yy[i]);
+            if ((threadIdx.x & 31) == 0) {
+                if (a & 0xffffu) atomicAdd(&sh[0][2 * i], a & 0xffffu);
+                if (a >> 16) atomicAdd(&sh[0][2 * i + 1], a >> 16);
+                if (b & 0xffffu) atomicAdd(&sh[1][2 * i], b & 0xffffu);
+                if (b >> 16) atomicAdd(&sh[1][2 * i + 1], b >> 16);
+                if (c & 0xffffu) atomicAdd(&sh[2][2 * i], c & 0xffffu);
+                if (c >> 16) atomicAdd(&sh[2][2 * i + 1], c >> 16);
+            }
+            tp[i] = pp[i] = yy[i] = 0u;
+        }
+    };
+
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long n16 = vec_ok ? n / 16 : 0;
-    for (long long i = tid; i < n16; i += stride) {
-        const uint4 pv = ld_stream_u4(pred + i * 16);
-        const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
-        if (sizeof(LabelT) == 1) {
-            const uint4 yv = ld_stream_u4(reinterpret_cast<const uint8_t*>(label) + i * 16);
-            const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) one((pw[w] >> (8 * j)) & 0xffu, (yw[w] >> (8 * j)) & 0xffu);
-        } else {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float4 yf = ld_stream_f4(reinterpret_cast<const float*>(label) + i * 16 + w * 4);
-                one(pw[w] & 0xffu, label_class<float>(yf.x));
-                one((pw[w] >> 8) & 0xffu, label_class<float>(yf.y));
-                one((pw[w] >> 16) & 0xffu, label_class<float>(yf.z));
-                one((pw[w] >> 24) & 0xffu, label_class<float>(yf.w));
+    const long long nchunks = vec_ok ? n / kDiceChunk : 0;
+    // every lane of a warp runs the same number of iterations (REDUX needs the full warp): the loop bound is
+    // per warp, lanes past the end work on an empty chunk
+    const long long warp_first = tid - (threadIdx.x & 31);
+    int iters = 0;
+    ChunkRegs<LabelT> cur, nxt;
+    if (tid < nchunks) cur.load(pred, label, tid);
+    for (long long i = tid; warp_first + (i - tid) < nchunks; i += stride) {
+        const bool have = i < nchunks;
+        const long long inext = i + stride;
+        if (inext < nchunks) nxt.load(pred, label, inext);  // in flight while this chunk is counted
+        if (have) {
+            unsigned pw[8], yw[8];
+            pw[0] = cur.p0.x, pw[1] = cur.p0.y, pw[2] = cur.p0.z, pw[3] = cur.p0.w;
+            pw[4] = cur.p1.x, pw[5] = cur.p1.y, pw[6] = cur.p1.z, pw[7] = cur.p1.w;
+            cur.label_words(yw);
+            if (has_wide_label(pw) || has_wide_label(yw)) {  // some label >= 16: voxel by voxel, re-read as bytes
+#pragma unroll 1
+                for (int v = 0; v < kDiceChunk; ++v)
+                    slow_one(pred[i * kDiceChunk + v], label_class<LabelT>(label[i * kDiceChunk + v]));
+            } else {
+                dice_chunk<KP>(pw, yw, tp, pp, yy);
             }
         }
-        pending += 16;
-        if (pending >= 240) {  // 8-bit fields hold 255
-            spill(tp_lo, tp_hi, sh[0]);
-            spill(p_lo, p_hi, sh[1]);
-            spill(y_lo, y_hi, sh[2]);
-            pending = 0;
+        cur = nxt;
+        if (++iters == kDiceFlushIters) {
+            flush();
+            iters = 0;
         }
     }
-    for (long long v = n16 * 16 + tid; v < n; v += stride) {
-        one(pred[v], label_class<LabelT>(label[v]));
-        if (++pending >= 240) {
-            spill(tp_lo, tp_hi, sh[0]);
-            spill(p_lo, p_hi, sh[1]);
-            spill(y_lo, y_hi, sh[2]);
-            pending = 0;
-        }
-    }
-    spill(tp_lo, tp_hi, sh[0]);
-    spill(p_lo, p_hi, sh[1]);
-    spill(y_lo, y_hi, sh[2]);
+    flush();
+    // scalar tail (and the whole array when a pointer is not 16-byte aligned)
+    for (long long v = nchunks * kDiceChunk + tid; v < n; v += stride) slow_one(pred[v], label_class<LabelT>(label[v]));
     __syncthreads();
     if (threadIdx.x < 48) {
         const int q = threadIdx.x / 16, c = threadIdx.x % 16;
         const unsigned v = sh[q][c];
         if (c < K && v) atomicAdd(reinterpret_cast<unsigned long long*>(counts) + q * K + c, static_cast<unsigned long long>(v));
+    }
+}
+
+template <typename LabelT>
+static void launch_dice(unsigned blocks, cudaStream_t s, const uint8_t* pred, const LabelT* label, long long n, int K,
+                        long long* counts, int vec_ok) {
+    switch ((K + 1) / 2) {
+        case 1: dice_kernel<LabelT, 1><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 2: dice_kernel<LabelT, 2><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 3: dice_kernel<LabelT, 3><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 4: dice_kernel<LabelT, 4><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 5: dice_kernel<LabelT, 5><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 6: dice_kernel<LabelT, 6><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 7: dice_kernel<LabelT, 7><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        default: dice_kernel<LabelT, 8><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
     }
 }
 
@@ -120,17 +170,17 @@ extern "C" int mss_dice_counts(const uint8_t* pred, const void* label, int32_t l
     MSS_REQUIRE(n_classes >= 1 && n_classes <= 16, MSS_E_UNSUPPORTED, "dice_counts: n_classes %d outside [1, 16]", n_classes);
     MSS_REQUIRE(label_dtype == 0 || label_dtype == 1, MSS_E_ARG, "dice_counts: label_dtype must be 0 (uint8) or 1 (float32)");
     // a block's shared histogram is 32-bit: bound the voxels one block can see below 2^32
-    long long blocks = (n_voxels / 16 + kDiceThreads - 1) / kDiceThreads + 1;
-    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    long long blocks = (n_voxels / kDiceChunk + kDiceThreads - 1) / kDiceThreads + 1;
+    if (blocks > 148LL * 4) blocks = 148LL * 4;
     MSS_REQUIRE(n_voxels / blocks < (1LL << 31), MSS_E_UNSUPPORTED, "dice_counts: volume too large for one call");
     const int vec_ok = reinterpret_cast<uintptr_t>(pred) % 16 == 0 && reinterpret_cast<uintptr_t>(label) % 16 == 0;
     cudaStream_t s = as_stream(stream);
     if (label_dtype == 0)
-        dice_kernel<uint8_t><<<static_cast<unsigned>(blocks), kDiceThreads, 0, s>>>(
-            pred, static_cast<const uint8_t*>(label), n_voxels, n_classes, counts, vec_ok);
+        launch_dice<uint8_t>(static_cast<unsigned>(blocks), s, pred, static_cast<const uint8_t*>(label), n_voxels, n_classes,
+                             counts, vec_ok);
     else
-        dice_kernel<float><<<static_cast<unsigned>(blocks), kDiceThreads, 0, s>>>(pred, static_cast<const float*>(label),
-                                                                                  n_voxels, n_classes, counts, vec_ok);
+        launch_dice<float>(static_cast<unsigned>(blocks), s, pred, static_cast<const float*>(label), n_voxels, n_classes,
+                           counts, vec_ok);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }

@@ -2,10 +2,17 @@
 // (replaces `output_image / count_map` of engine/utils.py:151 and the softmax -> D2H -> np.argmax -> uint8
 // of engine/test.py:140-141 / :81-82; the eval variant AsDiscrete(argmax=True) of engine/test.py:29).
 //
-// One thread owns 4 consecutive W voxels and streams the K class planes once (16-byte loads).  The
-// K-channel-replicated count_map of the reference (engine/utils.py:142,148) is never materialised:
-// the weight count of a voxel is re-derived from the geometry table and the (L2-resident) importance
-// map as the ascending fp32 sum over its covering windows - the same additions in the same order.
+// One thread owns 4 consecutive W voxels and streams the K class planes once (16-byte loads, KU planes
+// in flight per thread, three 256-thread CTAs per SM).  Three specialisations share the body:
+//   labels only      - the common case.  The first-max argmax is taken on the sums as stored: dividing
+//                      every class of a voxel by its (positive) weight count cannot reorder them, so the
+//                      count is not even computed; two classes can only collapse into a tie through the
+//                      rounding of the division, which is far inside the near-tie tolerance (counted).
+//   normalised logits - divides by the window-weight count (the K-channel-replicated count_map of the
+//                      reference, engine/utils.py:142,148, is never materialised: the count of a voxel is
+//                      re-derived from the geometry table and the L2-resident importance map as the
+//                      ascending fp32 sum over its covering windows - same additions, same order).
+//   probabilities    - adds the two softmax sweeps (engine/test.py:140); kept out of the hot variants.
 #include "common.cuh"
 #include "labels.cuh"
 
@@ -17,7 +24,6 @@ struct FinParams {
     Geo g;
     const float* logits;
     const float* imp;
-    int normalise;
     int box_lo[3];
     int box_n[3];
     int nq;
@@ -29,135 +35,169 @@ struct FinParams {
     unsigned long long* near_ties;
 };
 
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinParams p) {
+// ascending fp32 sum of the importance weights of all windows covering the 4 voxels at global (gd, gh, gw..gw+3)
+__device__ __forceinline__ void weight_count(const Geo& g, const float* __restrict__ imp, int gd, int gh, int gw,
+                                             const bool (&valid)[4], float (&cnt)[4]) {
+    const int rh = g.roi[1], rw = g.roi[2];
+    const int cvd = g.cover[0][gd], cvh = g.cover[1][gh];
+    int wlo = 0x7fffffff, whi = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (valid[e]) {
+            const int c = g.cover[2][gw + e];
+            wlo = min(wlo, c & 0xffff);
+            whi = max(whi, c >> 16);
+        }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cnt[e] = 0.f;
+    for (int id = cvd & 0xffff; id < (cvd >> 16); ++id)
+        for (int ih = cvh & 0xffff; ih < (cvh >> 16); ++ih) {
+            const float* row = imp + (static_cast<long long>(gd - g.starts[0][id]) * rh + (gh - g.starts[1][ih])) * rw;
+            for (int iw = wlo; iw < whi; ++iw) {
+                const int ww = gw - g.starts[2][iw];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (valid[e] && ww + e >= 0 && ww + e < rw) cnt[e] = __fadd_rn(cnt[e], __ldg(row + ww + e));
+            }
+        }
+}
+
+enum : int { kFinLabels = 0, kFinNormalise = 1, kFinProbs = 2 };
+
+template <int MODE, int KU>
+__global__ void __launch_bounds__(kFinThreads, MODE == kFinLabels ? 3 : 2) finalize_kernel(const __grid_constant__ FinParams p) {
     const Geo& g = p.g;
     const int t = blockIdx.x * kFinThreads + threadIdx.x;
-    if (t >= p.nq * p.box_n[1]) return;
+    const bool in_box = t < p.nq * p.box_n[1];
+    const int row = in_box ? t / p.nq : 0;
     const int ld = p.box_lo[0] + blockIdx.y;
-    const int lh = p.box_lo[1] + t / p.nq;
-    const int lw = p.box_lo[2] + (t % p.nq) * 4;
+    const int lh = p.box_lo[1] + row;
+    const int lw = p.box_lo[2] + (in_box ? t - row * p.nq : 0) * 4;
     const int b = blockIdx.z;
-    const int box_hi_w = p.box_lo[2] + p.box_n[2];
+    const int hi_w = min(p.box_lo[2] + p.box_n[2], g.ext[2]);
     bool valid[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) valid[e] = lw + e < box_hi_w && lw + e < g.ext[2];
-    if (!valid[0]) return;
+    for (int e = 0; e < 4; ++e) valid[e] = in_box && lw + e < hi_w;
+    unsigned ties = 0;
+    if (valid[0]) {
+        const int K = g.K;
+        const long long plane = static_cast<long long>(g.ext[1]) * g.pitch;
+        const long long cstride = static_cast<long long>(g.ext[0]) * plane;
+        const long long vox = static_cast<long long>(b) * K * cstride + static_cast<long long>(ld) * plane +
+                              static_cast<long long>(lh) * g.pitch + lw;
+        const float* src = p.logits + vox;
+        const bool full = valid[3];
 
-    float cnt[4] = {1.f, 1.f, 1.f, 1.f};
-    if (p.normalise) {
-        const int gd = ld + g.org[0], gh = lh + g.org[1], gw = lw + g.org[2];
-        const int rh = g.roi[1], rw = g.roi[2];
-        const int cvd = g.cover[0][gd], cvh = g.cover[1][gh];
-        int wlo = 0x7fffffff, whi = 0;
+        float cnt[4] = {1.f, 1.f, 1.f, 1.f};
+        const bool divide = MODE != kFinLabels && p.imp != nullptr;
+        if (divide) weight_count(g, p.imp, ld + g.org[0], lh + g.org[1], lw + g.org[2], valid, cnt);
+
+        ArgmaxState am[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (valid[e]) {
-                const int c = g.cover[2][gw + e];
-                wlo = min(wlo, c & 0xffff);
-                whi = max(whi, c >> 16);
-            }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) cnt[e] = 0.f;
-        for (int id = cvd & 0xffff; id < (cvd >> 16); ++id)
-            for (int ih = cvh & 0xffff; ih < (cvh >> 16); ++ih) {
-                const float* row = p.imp + (static_cast<long long>(gd - g.starts[0][id]) * rh + (gh - g.starts[1][ih])) * rw;
-                for (int iw = wlo; iw < whi; ++iw) {
-                    const int ww = gw - g.starts[2][iw];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (valid[e] && ww + e >= 0 && ww + e < rw) cnt[e] = __fadd_rn(cnt[e], __ldg(row + ww + e));
+        for (int e = 0; e < 4; ++e) am[e].reset();
+
+        auto consume = [&](float4 v, int k) {
+            if (MODE != kFinLabels) {
+                if (divide) {
+                    v.x = __fdiv_rn(v.x, cnt[0]);  // engine/utils.py:151
+                    v.y = __fdiv_rn(v.y, cnt[1]);
+                    v.z = __fdiv_rn(v.z, cnt[2]);
+                    v.w = __fdiv_rn(v.w, cnt[3]);
                 }
-            }
-    }
-
-    const long long plane = static_cast<long long>(g.ext[1]) * g.pitch;
-    const long long cstride = static_cast<long long>(g.ext[0]) * plane;
-    const long long vox = static_cast<long long>(b) * g.K * cstride + static_cast<long long>(ld) * plane +
-                          static_cast<long long>(lh) * g.pitch + lw;
-    const float* src = p.logits + vox;
-
-    ArgmaxState am[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) am[e].reset();
-    const bool full = valid[3];
-    constexpr int U = 8;
-    for (int k0 = 0; k0 < g.K; k0 += U) {
-        float4 v[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if (k0 + k < g.K) v[k] = *reinterpret_cast<const float4*>(src + (k0 + k) * cstride);
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if (k0 + k < g.K) {
-                if (p.normalise) {
-                    v[k].x = __fdiv_rn(v[k].x, cnt[0]);
-                    v[k].y = __fdiv_rn(v[k].y, cnt[1]);
-                    v[k].z = __fdiv_rn(v[k].z, cnt[2]);
-                    v[k].w = __fdiv_rn(v[k].w, cnt[3]);
-                }
-                am[0].push(v[k].x, k0 + k);
-                am[1].push(v[k].y, k0 + k);
-                am[2].push(v[k].z, k0 + k);
-                am[3].push(v[k].w, k0 + k);
                 if (p.logits_out != nullptr) {
-                    float* dst = p.logits_out + vox + (k0 + k) * cstride;
+                    float* dst = p.logits_out + vox + k * cstride;
                     if (full) {
-                        *reinterpret_cast<float4*>(dst) = v[k];
+                        *reinterpret_cast<float4*>(dst) = v;
                     } else {
-                        dst[0] = v[k].x;
-                        if (valid[1]) dst[1] = v[k].y;
-                        if (valid[2]) dst[2] = v[k].z;
+                        dst[0] = v.x;
+                        if (valid[1]) dst[1] = v.y;
+                        if (valid[2]) dst[2] = v.z;
                     }
                 }
             }
-    }
+            am[0].push(v.x, k);
+            am[1].push(v.y, k);
+            am[2].push(v.z, k);
+            am[3].push(v.w, k);
+        };
 
-    if (p.probs_out != nullptr) {
-        // softmax(dim=classes) = exp(x - max) / sum exp(x - max), second and third sweep over the planes
-        const float* nsrc = (p.logits_out != nullptr) ? p.logits_out + vox : src;
-        const bool renorm = p.normalise && p.logits_out == nullptr;
-        float m[4] = {am[0].best, am[1].best, am[2].best, am[3].best};
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < g.K; ++k) {
-            float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
-            float xv[4] = {x.x, x.y, x.z, x.w};
+        int k0 = 0;
+        for (; k0 + KU <= K; k0 += KU) {  // full groups: KU independent 16-byte loads in flight
+            float4 v[KU];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
-                s[e] += expf(xv[e] - m[e]);
+            for (int k = 0; k < KU; ++k) v[k] = ld_stream_f4(src + (k0 + k) * cstride);
+#pragma unroll
+            for (int k = 0; k < KU; ++k) consume(v[k], k0 + k);
+        }
+        if (k0 < K) {
+            float4 v[KU];
+#pragma unroll
+            for (int k = 0; k < KU; ++k)
+                if (k0 + k < K) v[k] = ld_stream_f4(src + (k0 + k) * cstride);
+#pragma unroll
+            for (int k = 0; k < KU; ++k)
+                if (k0 + k < K) consume(v[k], k0 + k);
+        }
+
+        if (MODE == kFinProbs && p.probs_out != nullptr) {
+            // softmax(dim=classes) = exp(x - max) / sum exp(x - max): second and third sweep over the planes
+            const float* nsrc = (p.logits_out != nullptr) ? p.logits_out + vox : src;
+            const bool renorm = divide && p.logits_out == nullptr;
+            const float m[4] = {am[0].best, am[1].best, am[2].best, am[3].best};
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < K; ++k) {
+                const float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
+                float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
+                    s[e] += expf(xv[e] - m[e]);
+                }
+            }
+            for (int k = 0; k < K; ++k) {
+                const float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
+                float xv[4] = {x.x, x.y, x.z, x.w};
+                float* dst = p.probs_out + vox + k * cstride;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
+                    if (valid[e]) dst[e] = expf(xv[e] - m[e]) / s[e];
+                }
             }
         }
-        for (int k = 0; k < g.K; ++k) {
-            float4 x = *reinterpret_cast<const float4*>(nsrc + k * cstride);
-            float xv[4] = {x.x, x.y, x.z, x.w};
-            float* dst = p.probs_out + vox + k * cstride;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (renorm) xv[e] = __fdiv_rn(xv[e], cnt[e]);
-                if (valid[e]) dst[e] = expf(xv[e] - m[e]) / s[e];
-            }
-        }
-    }
 
-    if (p.labels != nullptr) {
-        uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
-                       static_cast<long long>(lh) * p.label_pitch + lw;
-        unsigned packed = 0, ties = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (valid[e]) {
-                packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
-                ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
-            }
-        if (full && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
-            *reinterpret_cast<unsigned*>(lab) = packed;
-        } else {
+        if (p.labels != nullptr) {
+            uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
+                           static_cast<long long>(lh) * p.label_pitch + lw;
+            unsigned packed = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (valid[e]) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+                if (valid[e]) {
+                    packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
+                    ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
+                }
+            if (full && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
+                *reinterpret_cast<unsigned*>(lab) = packed;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (valid[e]) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+            }
         }
-        if (ties && p.near_ties != nullptr) atomicAdd(p.near_ties, static_cast<unsigned long long>(ties));
     }
+    // near-tie census: one atomic per warp that saw any
+    if (p.near_ties != nullptr) {
+        const unsigned warp_ties = __reduce_add_sync(0xffffffffu, ties);
+        if (warp_ties != 0u && (threadIdx.x & 31) == 0) atomicAdd(p.near_ties, static_cast<unsigned long long>(warp_ties));
+    }
+}
+
+template <int MODE>
+static void launch_fin(dim3 grid, cudaStream_t s, const FinParams& p) {
+    if (p.g.K % 7 == 0)
+        finalize_kernel<MODE, 7><<<grid, kFinThreads, 0, s>>>(p);
+    else
+        finalize_kernel<MODE, 8><<<grid, kFinThreads, 0, s>>>(p);
 }
 
 }  // namespace mss
@@ -192,8 +232,7 @@ extern "C" int mss_finalize_labels(const mss_layout_t* lay, const float* logits,
     MSS_REQUIRE(box_lo[2] % 4 == 0, MSS_E_ALIGN, "finalize_labels: box_lo W (%d) must be a multiple of 4", box_lo[2]);
     p.nq = (p.box_n[2] + 3) / 4;
     p.logits = logits;
-    p.imp = importance_map;
-    p.normalise = normalise;
+    p.imp = normalise ? importance_map : nullptr;
     p.labels = labels;
     p.label_pitch = label_pitch_w;
     p.logits_out = logits_out;
@@ -204,7 +243,13 @@ extern "C" int mss_finalize_labels(const mss_layout_t* lay, const float* logits,
     dim3 grid(static_cast<unsigned>((per_plane + kFinThreads - 1) / kFinThreads), static_cast<unsigned>(p.box_n[0]),
               static_cast<unsigned>(g.nb));
     MSS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MSS_E_UNSUPPORTED, "finalize_labels: box too large for one launch");
-    finalize_kernel<<<grid, kFinThreads, 0, as_stream(stream)>>>(p);
+    cudaStream_t s = as_stream(stream);
+    if (probs_out != nullptr)
+        launch_fin<kFinProbs>(grid, s, p);
+    else if (logits_out != nullptr)
+        launch_fin<kFinNormalise>(grid, s, p);
+    else
+        launch_fin<kFinLabels>(grid, s, p);  // labels only: the weight count cannot change the argmax
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }

@@ -20,14 +20,10 @@ struct ArgmaxState {
         poisoned = false;
     }
     __device__ __forceinline__ void push(float v, int k) {
-        if (!(v < __int_as_float(0x7f800000))) poisoned = true;  // NaN or +inf
-        if (v > best) {
-            second = best;
-            best = v;
-            idx = k;
-        } else if (v > second) {
-            second = v;
-        }
+        poisoned |= !(v < __int_as_float(0x7f800000));  // NaN or +inf
+        idx = v > best ? k : idx;                       // strictly greater: the first maximum keeps its index
+        second = fmaxf(second, fminf(best, v));         // branch-free top-2 (a NaN leaves both untouched)
+        best = fmaxf(best, v);
     }
     __device__ __forceinline__ int label() const { return poisoned ? 0 : idx; }
     // top-2 gap relative to the larger magnitude strictly below tol

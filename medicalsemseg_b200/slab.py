@@ -157,7 +157,7 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
     windows into raw weighted sums over its buffer box.  Returns the Stitcher (``.acc`` is the buffer).
     ``volume`` is the full volume, or only this rank's slab ``[buf_lo, buf_hi)`` when ``volume_is_slab``."""
     from .importance import importance_map as build_imp
-    from .inferer import StitchPlan, Stitcher
+    from .inferer import StitchPlan, Stitcher, _tma_ready
 
     dev = torch.device("cuda", torch.cuda.current_device())
     ax, nb = part.axis, volume.shape[0]
@@ -171,7 +171,7 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
     src = volume if volume_is_slab else _region(volume, ax, origin[ax], origin[ax] + extent[ax])
     if tuple(src.shape[2:]) != tuple(extent):
         raise ValueError(f"slab has spatial shape {tuple(src.shape[2:])}, expected {tuple(extent)}")
-    slab = src.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    slab = _tma_ready(src.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), grid, cval)
     imp = build_imp(grid.roi, mode, sigma_scale, dev)
     st = Stitcher(plan, imp, fuse=_lib.FUSE_NONE, sw_batch=sw_batch_size, tie_tol=tie_tol, group_bytes=group_bytes,
                   stats=stats, time_kernels=time_kernels)
@@ -180,9 +180,7 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
         stats._near_ties = st.near
     if affine is not None:
         affine = affine.to(dev)
-    for first in range(0, st.total, sw_batch_size):
-        n = min(sw_batch_size, st.total - first)
-        patches, centers = st.extract(slab, first, n, cval, vol_origin=origin)
+    for _first, n, patches, centers in st.batches(slab, cval, vol_origin=origin):
         if sw_batch_size == 1:
             centers = centers.unsqueeze(0)
         with st.timer("predictor"):

@@ -1,0 +1,78 @@
+// Test-only: runs the bit-sliced per-chunk logic of the vote and Dice kernels (medicalsemseg_b200/csrc/bitslice.cuh,
+// the very code the kernels inline) on the CPU, so the CPU suite can check it against the oracle without a GPU.
+// Built by tests/test_bitslice_host.py with g++ into tests/_build/; never loaded by the product.
+#include <cstdint>
+#include <cstring>
+
+#include "../../medicalsemseg_b200/csrc/bitslice.cuh"
+
+using namespace mss;
+
+template <int M>
+static void vote_all(const uint8_t* const* maps, int K, long long nchunks, uint8_t* out) {
+    for (long long i = 0; i < nchunks; ++i) {
+        unsigned w[M][8], res[8];
+        for (int m = 0; m < M; ++m) std::memcpy(w[m], maps[m] + i * 32, 32);
+        vote_chunk<M>(w, K, res);
+        std::memcpy(out + i * 32, res, 32);
+    }
+}
+
+extern "C" int host_vote_chunks(const uint8_t* const* maps, int M, int K, long long n_voxels, uint8_t* out) {
+    const long long nchunks = n_voxels / 32;
+    switch (M) {
+        case 1: vote_all<1>(maps, K, nchunks, out); break;
+        case 2: vote_all<2>(maps, K, nchunks, out); break;
+        case 3: vote_all<3>(maps, K, nchunks, out); break;
+        case 4: vote_all<4>(maps, K, nchunks, out); break;
+        case 5: vote_all<5>(maps, K, nchunks, out); break;
+        case 6: vote_all<6>(maps, K, nchunks, out); break;
+        case 7: vote_all<7>(maps, K, nchunks, out); break;
+        case 8: vote_all<8>(maps, K, nchunks, out); break;
+        default: return -1;
+    }
+    return 0;
+}
+
+// counts[3][16] (TP, P, Y), all labels must be < 16
+extern "C" int host_dice_chunks(const uint8_t* pred, const uint8_t* label, int K, long long n_voxels, long long* counts) {
+    const long long nchunks = n_voxels / 32;
+    unsigned tp[8] = {0}, pp[8] = {0}, yy[8] = {0};
+    auto flush = [&]() {
+        for (int i = 0; i < 8; ++i) {
+            counts[0 * 16 + 2 * i] += tp[i] & 0xffffu, counts[0 * 16 + 2 * i + 1] += tp[i] >> 16;
+            counts[1 * 16 + 2 * i] += pp[i] & 0xffffu, counts[1 * 16 + 2 * i + 1] += pp[i] >> 16;
+            counts[2 * 16 + 2 * i] += yy[i] & 0xffffu, counts[2 * 16 + 2 * i + 1] += yy[i] >> 16;
+            tp[i] = pp[i] = yy[i] = 0;
+        }
+    };
+    int iters = 0;
+    for (long long i = 0; i < nchunks; ++i) {
+        unsigned pw[8], yw[8];
+        std::memcpy(pw, pred + i * 32, 32);
+        std::memcpy(yw, label + i * 32, 32);
+        if (has_wide_label(pw) || has_wide_label(yw)) return -2;
+        switch ((K + 1) / 2) {
+            case 1: dice_chunk<1>(pw, yw, tp, pp, yy); break;
+            case 2: dice_chunk<2>(pw, yw, tp, pp, yy); break;
+            case 3: dice_chunk<3>(pw, yw, tp, pp, yy); break;
+            case 4: dice_chunk<4>(pw, yw, tp, pp, yy); break;
+            case 5: dice_chunk<5>(pw, yw, tp, pp, yy); break;
+            case 6: dice_chunk<6>(pw, yw, tp, pp, yy); break;
+            case 7: dice_chunk<7>(pw, yw, tp, pp, yy); break;
+            default: dice_chunk<8>(pw, yw, tp, pp, yy); break;
+        }
+        if (++iters == 2040) flush(), iters = 0;  // per-thread 16-bit halves: 2040 * 32 < 65536
+    }
+    flush();
+    return 0;
+}
+
+extern "C" void host_bitplanes_roundtrip(const uint8_t* in32, uint8_t* out32, unsigned* planes4) {
+    unsigned w[8], q[4], r[8];
+    std::memcpy(w, in32, 32);
+    bitplanes32(w, q);
+    std::memcpy(planes4, q, 16);
+    labels_from_bitplanes32(q, r);
+    std::memcpy(out32, r, 32);
+}

@@ -145,3 +145,68 @@ def test_logits_to_labels_probs_and_ties():
     ok = torch.isfinite(logits).all(1, keepdim=True).expand_as(logits)
     assert torch.allclose(probs[ok], torch.softmax(logits, 1)[ok], rtol=1e-5, atol=1e-7)
     assert st.near_ties >= 1
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 15])
+@pytest.mark.parametrize("k", [2, 3, 14, 16])
+def test_majority_vote_all_ensemble_sizes(m, k):
+    """M <= 8 runs the bit-sliced kernel, above that the scalar one; labels 16..255 (legal, they match no class)
+    force the per-chunk scalar path inside the sliced kernel."""
+    rs = np.random.RandomState(1000 * m + k)
+    n = 32 * 1031 + 19  # chunks plus a scalar tail
+    base = rs.randint(0, k, n).astype(np.uint8)
+    maps = []
+    for _ in range(m):
+        noise = rs.randint(0, 16, n).astype(np.uint8)
+        mp = np.where(rs.random_sample(n) < 0.35, noise, base)
+        mp[rs.randint(0, n, 40)] = rs.randint(16, 256, 40)  # sprinkle wide labels
+        maps.append(np.ascontiguousarray(mp.astype(np.uint8)))
+    got = mss.majority_vote([torch.from_numpy(a).cuda() for a in maps], k).cpu().numpy()
+    assert np.array_equal(got, ovote.majority_vote(maps, k))
+
+
+def test_dice_counts_wide_labels_and_uniform():
+    rs = np.random.RandomState(9)
+    n = 32 * 70001 + 7
+    k = 14
+    pred = rs.randint(0, k, n).astype(np.uint8)
+    lab = np.where(rs.random_sample(n) < 0.7, pred, rs.randint(0, k, n)).astype(np.uint8)
+    pred[rs.randint(0, n, 500)] = rs.randint(16, 256, 500)
+    lab[rs.randint(0, n, 500)] = rs.randint(16, 256, 500)
+    got = mss.dice_counts(torch.from_numpy(pred).cuda(), torch.from_numpy(lab).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, odice.dice_counts(pred, lab, k))
+    # float labels that are not integers / negative / huge belong to no class
+    labf = lab.astype(np.float32)
+    labf[::1001] = 2.5
+    labf[5::1003] = -1.0
+    labf[7::1009] = 1e9
+    want_lab = lab.copy()
+    want_lab[::1001] = 255
+    want_lab[5::1003] = 255
+    want_lab[7::1009] = 255
+    got = mss.dice_counts(torch.from_numpy(pred).cuda(), torch.from_numpy(labf).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, odice.dice_counts(pred, want_lab, k))
+    # one class everywhere: every thread's packed counters see the maximum load
+    full = torch.full((512 * 512 * 200,), 3, dtype=torch.uint8, device="cuda")
+    got = mss.dice_counts(full, full, k).cpu().numpy()
+    assert got[0, 3] == full.numel() and got[1, 3] == full.numel() and got[2, 3] == full.numel() and got.sum() == 3 * full.numel()
+
+
+def test_extract_ahead_equals_per_batch():
+    rs = np.random.RandomState(2)
+    vol = torch.from_numpy(rs.standard_normal((2, 2, 40, 36, 44)).astype(np.float32)).cuda()
+    plan = inferer.get_plan((40, 36, 44), 16, 0.5, vol.device, 2)
+    imp = torch.ones(plan.grid.roi, device=vol.device)
+    per_window = 4 * 2 * 16 ** 3
+    got = {}
+    for budget in (per_window, 7 * per_window, 1 << 30):  # one batch per launch, ragged groups, everything at once
+        st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LOGITS, sw_batch=3, extract_bytes=budget)
+        ps, cs, firsts = [], [], []
+        for first, n, p, c in st.batches(vol, 0.0):
+            assert p.is_contiguous() and p.shape[0] == n
+            ps.append(p.clone()), cs.append(c.clone()), firsts.append(first)
+        assert firsts == list(range(0, st.total, 3))
+        got[budget] = (torch.cat(ps), torch.cat(cs))
+    ref = got[per_window]
+    for budget, (p, c) in got.items():
+        assert torch.equal(p, ref[0]) and torch.equal(c, ref[1])
