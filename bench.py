@@ -173,6 +173,7 @@ def main() -> None:
     ap.add_argument("--sw-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-gib", type=float, default=None, help="logits held per accumulate launch (default: auto)")
+    ap.add_argument("--block-dims", default=None, help="wholebody, N > 1: ranks per axis as DxHxW (default: best balance)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

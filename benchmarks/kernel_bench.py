@@ -106,17 +106,12 @@ def main():
 
     if want("extract"):
         st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LABELS, sw_batch=B)
-        for tma in (True, False):
-            st.use_tma = tma
-            med, mn = timed(lambda: st.extract(vol, 0, B, 0.0), args.reps, flush)
-            report(f"extract B={B} tma={int(tma)}", 8 * B * cin * r, med, mn, "one predictor batch")
-        for big in (40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))):
-            st.use_tma = True
-            med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
-            report(f"extract B={big} tma=1", 8 * big * cin * r, med, mn, "extract-ahead group" if big > 40 else "")
-            st.use_tma = False
-            med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
-            report(f"extract B={big} tma=0", 8 * big * cin * r, med, mn)
+        names = {1: "auto (TMA if W starts are 16-byte aligned)", 0: "shifted-vector", 2: "scalar"}
+        for big in (B, 40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))):
+            for mode in (1, 0, 2):
+                st.use_tma = mode
+                med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
+                report(f"extract B={big} mode={mode}", 8 * big * cin * r, med, mn, names[mode])
 
     if want("accumulate") or want("accumulate_rmw") or want("finalize"):
         n_batches = -(-n_win // B)
@@ -181,6 +176,14 @@ def main():
         report(f"dice_counts u8 labels K={k}", 2 * v, med, mn)
         med, mn = timed(lambda: mss.dice_counts(pred, labf, k, out=out), args.reps, flush)
         report(f"dice_counts f32 labels K={k}", 5 * v, med, mn)
+
+    if want("resample"):
+        from medicalsemseg_b200.resample import resample_3d
+        lab = torch.randint(0, k, (d, h, w), dtype=torch.uint8, device=dev)
+        for tgt in ((d, h, int(w * 0.735)), (int(d * 1.25), int(h * 1.25), w)):
+            vo = tgt[0] * tgt[1] * tgt[2]
+            med, mn = timed(lambda: resample_3d(lab, tgt), args.reps, flush)
+            report(f"resample_3d -> {tgt[0]}x{tgt[1]}x{tgt[2]}", v + vo, med, mn, "uint8 gather: V_in + V_out bytes")
 
     if want("halo"):
         rows, length = k * 512, 512 * 48

@@ -1,5 +1,6 @@
 """bench.py --workload wholebody with N > 1 ranks: ONE 512x512x1024 volume (BASELINE.json configs[2]) partitioned into
-slabs along its long axis, halo accumulators exchanged over NCCL, every rank finalising the planes it owns.
+blocks of windows (medicalsemseg_b200/block.py: 1-D slabs are the special case; 2x2x2 on 8 ranks), halo accumulators
+exchanged over NCCL axis by axis, every rank finalising the box it owns.
 Strong scaling: total work is fixed, value = voxels of the whole volume / max-over-ranks step time."""
 from __future__ import annotations
 
@@ -14,33 +15,33 @@ def run_wholebody(args, wl, rank, world, dev, dist) -> None:
     import medicalsemseg_b200 as mss
     from bench import METRIC, ROI, ClockSampler, peaks, physical_gpu_index
     from benchmarks.backbones import build_backbone
-    from medicalsemseg_b200 import slab
+    from medicalsemseg_b200 import block
     from medicalsemseg_b200.grid import make_grid
 
     nb, cin, d, h, w = wl["shape"]
     k = wl["k"]
     model = build_backbone(wl["backbone"], cin, k).to(dev)
     grid = make_grid((d, h, w), ROI, wl["overlap"])
-    part = slab.partition(grid, world)
-    ax = part.axis
-    # every rank holds only its slab of the synthetic volume (same global random field: seeded per plane block)
-    ext = list((d, h, w))
-    ext[ax] = part.buf_hi[rank] - part.buf_lo[rank]
+    dims = None if not getattr(args, "block_dims", None) else tuple(int(x) for x in args.block_dims.split("x"))
+    part = block.block_partition(grid, world, dims)
+    # every rank holds only its block of the synthetic volume
+    blo, bhi = part.box(rank, "buf")
+    ext = [hh - ll for ll, hh in zip(blo, bhi)]
     gen = torch.Generator().manual_seed(1000 + rank)
     host_slab = torch.randn([nb, cin] + ext, generator=gen).pin_memory()
-    own_planes = part.own_hi[rank] - part.own_lo[rank]
-    own_shape = [nb, d, h, w]
-    own_shape[1 + ax] = own_planes
-    host_labels = torch.empty(own_shape, dtype=torch.uint8).pin_memory()
+    olo, ohi = part.box(rank, "own")
+    host_labels = torch.empty([nb] + [hh - ll for ll, hh in zip(olo, ohi)], dtype=torch.uint8).pin_memory()
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     def step(slab_any, stats=None, time_kernels=False):
         with torch.no_grad():
-            st = slab.local_pass(slab_any, model, grid, part, rank, "gaussian", sw_batch_size=args.sw_batch, stats=stats,
-                                 time_kernels=time_kernels, volume_is_slab=True)
+            st = block.local_pass(slab_any, model, grid, part, rank, "gaussian", sw_batch_size=args.sw_batch, stats=stats,
+                                  time_kernels=time_kernels, volume_is_block=True)
             with st.timer("halo"):
-                slab.exchange_halos(st.acc, part, rank, None)
-            return slab.finalize_owned(st, part, rank)
+                halo_bytes[0] = block.exchange_halos(st.acc, part, rank, None)
+            return block.finalize_owned(st, part, rank)
+
+    halo_bytes = [0]
 
     def barrier():
         dist.barrier()
@@ -97,8 +98,9 @@ def run_wholebody(args, wl, rank, world, dev, dist) -> None:
             "config": {"workload": "wholebody", "baseline_config": wl["cfg"], "shape": list(wl["shape"]), "roi": ROI,
                        "overlap": wl["overlap"], "classes": k, "blend": "gaussian", "windows": grid.n_windows,
                        "sw_batch": args.sw_batch, "backbone": wl["backbone"] + " (random init, seed 13, fp32 eager torch)",
-                       "partition": {"axis": ax, "window_starts_per_rank": [hi - lo for lo, hi in zip(part.win_lo, part.win_hi)],
-                                     "halo_planes": [part.halo(i)[1] - part.halo(i)[0] for i in range(world)]},
+                       "partition": {"ranks_per_axis_dhw": list(part.dims),
+                                     "windows_per_rank": [part.n_windows(i) for i in range(world)],
+                                     "halo_bytes_received_rank0": int(halo_bytes[0])},
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": v * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": host_slab.numel() * 4, "d2h_bytes_per_step": host_labels.numel(),

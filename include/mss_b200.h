@@ -119,9 +119,10 @@ int mss_importance_map(float* map_out, const int32_t roi[3], int32_t mode, const
  * relative centres (engine/utils.py:126-130) into centers_out[n_windows, 3].
  * `volume` is [Nb, Cin, vol_extent] fp32, contiguous; its voxel (0,0,0) sits at stitched-frame
  * coordinate vol_origin (= the reference's pad offsets, engine/utils.py:98-103); anything outside
- * reads as `cval`.  Uses TMA 3-D tiled copies when the layout allows (W and roi_w multiples of 4,
- * 16-byte aligned bases, window inside the volume), plain vector loads otherwise.
- * use_tma: 1 = auto, 0 = force the non-TMA kernel. */
+ * reads as `cval`.  Three kernels: TMA 3-D tiled copies (W, roi_w multiples of 4, 16-byte aligned bases, every
+ * window inside the volume and starting on a multiple of 4 along W); a shifted-vector copy for the same layout
+ * with arbitrary W starts; scalar loads for everything else (constant pad, odd row pitch).
+ * use_tma: 1 = auto, 0 = never TMA (shifted-vector or scalar), 2 = scalar kernel only. */
 int mss_extract_patches(const float* volume, const int32_t vol_origin[3], const int32_t vol_extent[3],
                         int32_t n_channels, float cval, const mss_layout_t* lay, int64_t first_window,
                         int32_t n_windows, float* patches_out, float* centers_out, int32_t use_tma,
@@ -169,6 +170,22 @@ int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype,
  * independent row pitches (the receiving rank adds its neighbour's partial sums). */
 int mss_halo_add(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t n_rows,
                  int64_t row_len, void* stream);
+
+/* ---- after the argmax: back to the original voxel grid ---------------- */
+
+/* Per-axis source-index table of scipy.ndimage.zoom(order=0, prefilter=False, mode='constant') as the
+ * reference calls it (utils/misc.py:420-425): table_out[k] = floor(k*zoom + 0.5) with
+ * zoom = (n_in-1)/(n_out-1) in float64 (1.0 when n_out == 1), or -1 where k*zoom leaves [0, n_in-1]
+ * (scipy then writes cval = 0; rounding makes this hit the last index of some size pairs).  Host only. */
+int mss_zoom_index_table(int32_t n_in, int32_t n_out, int32_t* table_out);
+
+/* Nearest-neighbour resampling of uint8 label maps [n_volumes, in_dims] -> [n_volumes, out_dims]
+ * (utils/misc.py:420-425 resample_3d, called at engine/test.py:143-147): out[x,y,z] =
+ * in[index_x[x], index_y[y], index_z[z]], 0 where any index is -1.  index_* are DEVICE int32 tables of
+ * out_dims[a] entries, as produced by mss_zoom_index_table. */
+int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_dims[3], uint8_t* labels_out,
+                         const int32_t out_dims[3], int64_t n_volumes, const int32_t* index_x,
+                         const int32_t* index_y, const int32_t* index_z, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,275 @@
+"""Block (up to 3-D) partition of ONE large volume over the GPUs of a box: the general form of slab.py.
+
+The 1-D slab split of BASELINE.json configs[2] (21 window starts along the long axis over 8 ranks = 3/3/3/3/3/2/2/2)
+caps the speed-up at 2100 / 300 = 7.0x because window starts only come in whole layers of 100 windows.  Cutting the
+window-index box along several axes balances better: 2 x 2 x 2 blocks of the 10 x 10 x 21 grid hold at most
+5 * 5 * 11 = 275 windows (7.64x), 1 x 2 x 2 blocks on 4 ranks 550 instead of 600.  ``choose_dims`` picks the
+factorisation of the world size with the smallest maximum window count (ties: fewer cut axes, i.e. less halo).
+
+Per axis everything is the 1-D logic of slab.py (``SlabPartition``: window-start ranges, buffer box, owned planes,
+halo = planes written beyond the ownership).  Halos are reduced one axis after the other - W, then H, then D: a rank
+ships the planes beyond its ownership along the axis over the FULL extent of its buffer in the axes not yet reduced
+(and only its owned range in the axes already done) to its +1 neighbour along that axis, which adds them
+(``mss_halo_add``).  Contributions for diagonal neighbours travel in two or three hops.  Ranks that differ only in
+their coordinate along the axis have identical buffer extents in the other axes, so the exchanged boxes match.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .grid import WindowGrid, make_grid
+from .slab import SlabPartition, cuda_halo_add, partition
+
+
+@dataclass
+class BlockPartition:
+    dims: Tuple[int, int, int]       # ranks along D, H, W; world = product
+    axes: List[SlabPartition]        # 1-D partition of every axis (world = dims[a])
+
+    @property
+    def world(self) -> int:
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+    def coords(self, rank: int) -> Tuple[int, int, int]:
+        pd, ph, pw = self.dims
+        return rank // (ph * pw), (rank // pw) % ph, rank % pw
+
+    def rank_of(self, coords: Sequence[int]) -> int:
+        return (coords[0] * self.dims[1] + coords[1]) * self.dims[2] + coords[2]
+
+    def n_windows(self, rank: int) -> int:
+        c = self.coords(rank)
+        n = 1
+        for a in range(3):
+            n *= self.axes[a].win_hi[c[a]] - self.axes[a].win_lo[c[a]]
+        return n
+
+    def box(self, rank: int, what: str) -> Tuple[List[int], List[int]]:
+        """Global (lo, hi) per axis of rank's ``"buf"`` (accumulator) or ``"own"`` (finalised) box."""
+        c = self.coords(rank)
+        lo = [getattr(self.axes[a], what + "_lo")[c[a]] for a in range(3)]
+        hi = [getattr(self.axes[a], what + "_hi")[c[a]] for a in range(3)]
+        return lo, hi
+
+    def win_box(self, rank: int) -> Tuple[List[int], List[int]]:
+        c = self.coords(rank)
+        return [self.axes[a].win_lo[c[a]] for a in range(3)], [self.axes[a].win_hi[c[a]] for a in range(3)]
+
+
+def _factorisations(world: int) -> List[Tuple[int, int, int]]:
+    out = []
+    for pd in range(1, world + 1):
+        if world % pd:
+            continue
+        for ph in range(1, world // pd + 1):
+            if (world // pd) % ph:
+                continue
+            out.append((pd, ph, world // pd // ph))
+    return out
+
+
+def choose_dims(grid: WindowGrid, world: int) -> Tuple[int, int, int]:
+    """Factorisation of ``world`` over (D, H, W) with the smallest maximum window count per rank; ties go to fewer
+    cut axes, then to cutting the longest axes."""
+    ns = grid.n_starts
+    best, best_key = None, None
+    for dims in _factorisations(world):
+        if any(dims[a] > ns[a] for a in range(3)):
+            continue
+        load = 1
+        for a in range(3):
+            load *= -(-ns[a] // dims[a])
+        key = (load, sum(1 for p in dims if p > 1), tuple(-dims[a] * ns[a] for a in range(3)))
+        if best_key is None or key < best_key:
+            best, best_key = dims, key
+    if best is None:
+        raise ValueError(f"a {ns} window grid cannot be partitioned over {world} ranks")
+    return best
+
+
+def block_partition(grid: WindowGrid, world: int, dims: Optional[Sequence[int]] = None) -> BlockPartition:
+    dims = tuple(dims) if dims is not None else choose_dims(grid, world)
+    if len(dims) != 3 or dims[0] * dims[1] * dims[2] != world:
+        raise ValueError(f"dims {dims} do not multiply to the world size {world}")
+    return BlockPartition(dims, [partition(grid, dims[a], axis=a) for a in range(3)])
+
+
+def _box_view(t: torch.Tensor, lo: Sequence[int], hi: Sequence[int]) -> torch.Tensor:
+    """View of the buffer-local box [lo, hi) of a ``[..., D, H, W]`` tensor."""
+    return t[(Ellipsis, slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2], hi[2]))]
+
+
+def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: WindowGrid, part: BlockPartition,
+               rank: int, mode: Any = "gaussian", *, sw_batch_size: int = 4, sigma_scale: Any = 0.125, cval: float = 0.0,
+               affine: Optional[torch.Tensor] = None, tuple_input: bool = False, tie_tol: float = 1e-5,
+               stats: Any = None, time_kernels: bool = False, group_bytes: Optional[int] = None,
+               volume_is_block: bool = False):
+    """Everything rank `rank` does before the exchange: block copy, extract -> backbone -> accumulate of its own
+    windows into raw weighted sums over its buffer box.  Returns the Stitcher (``.acc`` is the buffer).
+    ``volume`` is the full volume, or only this rank's buffer box of it when ``volume_is_block``."""
+    from .importance import importance_map as build_imp
+    from .inferer import StitchPlan, Stitcher, _tma_ready
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb = volume.shape[0]
+    origin, hi = part.box(rank, "buf")
+    extent = [h - l for l, h in zip(origin, hi)]
+    win_lo, win_hi = part.win_box(rank)
+    plan = StitchPlan(grid, dev, nb, win_lo, win_hi, origin, extent)
+    src = volume if volume_is_block else _box_view(volume, origin, hi)
+    if tuple(src.shape[2:]) != tuple(extent):
+        raise ValueError(f"block has spatial shape {tuple(src.shape[2:])}, expected {tuple(extent)}")
+    block = _tma_ready(src.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), grid, cval)
+    imp = build_imp(grid.roi, mode, sigma_scale, dev)
+    st = Stitcher(plan, imp, fuse=_lib.FUSE_NONE, sw_batch=sw_batch_size, tie_tol=tie_tol, group_bytes=group_bytes,
+                  stats=stats, time_kernels=time_kernels)
+    if stats is not None:
+        stats.n_windows = st.total
+        stats._near_ties = st.near
+    if affine is not None:
+        affine = affine.to(dev)
+    for _first, n, patches, centers in st.batches(block, cval, vol_origin=origin):
+        if sw_batch_size == 1:
+            centers = centers.unsqueeze(0)
+        with st.timer("predictor"):
+            logits = model((patches, centers, affine) if tuple_input else patches)
+        st.push(logits, n)
+        if stats is not None:
+            stats.n_predictor_calls += 1
+    st.flush()
+    return st
+
+
+def exchange_halos(acc: torch.Tensor, part: BlockPartition, rank: int, group: Any = None,
+                   add_fn: Callable[[torch.Tensor, torch.Tensor], None] = cuda_halo_add,
+                   order: Sequence[int] = (2, 1, 0)) -> int:
+    """Axis-by-axis nearest-neighbour halo reduction on ``acc[Nb, K, *buffer]``.  Returns bytes received."""
+    import torch.distributed as dist
+
+    c = part.coords(rank)
+    buf_lo, buf_hi = part.box(rank, "buf")
+    own_lo, own_hi = part.box(rank, "own")
+    lo = [0, 0, 0]                                    # buffer-local box still carrying live partial sums
+    hi = [h - l for l, h in zip(buf_lo, buf_hi)]
+    received = 0
+
+    def peer(a: int, step: int) -> int:
+        cc = list(c)
+        cc[a] += step
+        r = part.rank_of(cc)
+        return dist.get_global_rank(group, r) if group is not None else r
+
+    for a in order:
+        p1, i = part.axes[a], c[a]
+        if p1.world > 1:
+            send_lo, send_hi = p1.halo(i)
+            reqs, keep = [], []
+
+            def do_send() -> None:
+                if i + 1 < p1.world and send_hi > send_lo:
+                    blo, bhi = list(lo), list(hi)
+                    blo[a], bhi[a] = send_lo - buf_lo[a], send_hi - buf_lo[a]
+                    buf = _box_view(acc, blo, bhi).contiguous()
+                    keep.append(buf)
+                    reqs.append(dist.isend(buf, peer(a, +1), group=group))
+
+            early = not p1.halo_depends_on_previous(i)
+            if early:
+                do_send()
+            if i > 0:
+                rlo, rhi = p1.halo(i - 1)
+                if rhi > rlo:
+                    blo, bhi = list(lo), list(hi)
+                    blo[a], bhi[a] = rlo - buf_lo[a], rhi - buf_lo[a]
+                    view = _box_view(acc, blo, bhi)
+                    tmp = torch.empty(view.shape, dtype=acc.dtype, device=acc.device)
+                    dist.recv(tmp, peer(a, -1), group=group)
+                    add_fn(view, tmp)
+                    received += tmp.numel() * tmp.element_size()
+            if not early:
+                do_send()
+            for r in reqs:
+                r.wait()
+        # from here on only the owned planes along `a` carry anything this rank still needs
+        lo[a], hi[a] = own_lo[a] - buf_lo[a], own_hi[a] - buf_lo[a]
+    return received
+
+
+def finalize_owned(st: Any, part: BlockPartition, rank: int, tie_tol: float = 1e-5,
+                   logits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Normalise (weight count of the GLOBAL grid) + argmax of the box rank `rank` owns -> uint8 ``[Nb, own box]``."""
+    from .inferer import labels_from_logits
+
+    origin = st.plan.origin
+    own_lo, own_hi = part.box(rank, "own")
+    lo = [own_lo[a] - origin[a] for a in range(3)]
+    hi = [own_hi[a] - origin[a] for a in range(3)]
+    w_shift = lo[2] % 4  # the kernel wants a box start that is a multiple of 4 along W: recompute a few voxels, crop
+    lo[2] -= w_shift
+    buf = labels_from_logits(st.acc, st, tie_tol=tie_tol, normalise=True, box=(lo, hi), logits_out=logits_out)
+    lo[2] += w_shift
+    return buf[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+
+
+def sliding_window_infer_blocks(
+    volume: torch.Tensor,
+    model: Callable[..., torch.Tensor],
+    roi: Any = 96,
+    overlap: float = 0.5,
+    mode: Any = "gaussian",
+    *,
+    group: Any = None,
+    dims: Optional[Sequence[int]] = None,
+    sw_batch_size: int = 4,
+    sigma_scale: Any = 0.125,
+    cval: float = 0.0,
+    affine: Optional[torch.Tensor] = None,
+    tuple_input: Optional[bool] = None,
+    tie_tol: float = 1e-5,
+    gather: bool = False,
+    stats: Any = None,
+    time_kernels: bool = False,
+    group_bytes: Optional[int] = None,
+) -> Tuple[torch.Tensor, Tuple[List[int], List[int]], BlockPartition]:
+    """Block-partitioned ``sliding_window_infer`` over the ranks of ``group``.
+
+    ``volume`` is the FULL ``[Nb, C, D, H, W]`` volume (host or device, identical on every rank); each rank copies
+    only its block to its GPU.  Returns ``(labels, (own_lo, own_hi), partition)`` where ``labels`` holds this rank's
+    owned box ``[Nb, ...]`` - or the whole label map on every rank when ``gather=True``.
+    """
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if volume.dim() != 5:
+        raise ValueError("volume must be [N, C, D, H, W]")
+    nb = volume.shape[0]
+    grid = make_grid(tuple(volume.shape[2:]), roi, overlap)
+    if grid.padded:
+        raise ValueError("block partitioning expects a volume at least one window large on every axis")
+    part = block_partition(grid, world, dims)
+    if tuple_input is None:
+        tuple_input = affine is not None
+    st = local_pass(volume, model, grid, part, rank, mode, sw_batch_size=sw_batch_size, sigma_scale=sigma_scale, cval=cval,
+                    affine=affine, tuple_input=tuple_input, tie_tol=tie_tol, stats=stats, time_kernels=time_kernels,
+                    group_bytes=group_bytes)
+    with st.timer("halo"):
+        halo_bytes = exchange_halos(st.acc, part, rank, group)
+    if stats is not None:
+        stats.halo_bytes = halo_bytes
+    own = finalize_owned(st, part, rank, tie_tol)
+    own_box = part.box(rank, "own")
+    if not gather:
+        return own, own_box, part
+    full = torch.empty((nb,) + grid.image_size, dtype=torch.uint8, device=dev)
+    mine = own.contiguous()
+    for r in range(world):  # boxes differ in size: one broadcast per owner
+        lo, hi = part.box(r, "own")
+        buf = mine if r == rank else torch.empty([nb] + [h - l for l, h in zip(lo, hi)], dtype=torch.uint8, device=dev)
+        dist.broadcast(buf, dist.get_global_rank(group, r) if group is not None else r, group=group)
+        _box_view(full, lo, hi).copy_(buf)
+    return full, own_box, part

@@ -5,7 +5,11 @@
 // rank-4 tensor maps.  Each CTA is one warp whose elected lane drives a ring of shared-memory stages:
 // cp.async.bulk.tensor (global -> smem, mbarrier complete_tx) followed by cp.async.bulk.tensor
 // (smem -> global, bulk_group).  No thread ever touches the data; the SMs only issue descriptors.
-// Fallback path (W or roi_w not a multiple of 4, unaligned base, or a window that reaches into the
+// TMA wants every box to start on a 16-byte boundary of the innermost dimension, so it serves the groups whose
+// W-starts are all multiples of 4 (every regular start of a 96^3 / overlap-.5 grid; a clamped last start such as
+// BraTS' 155 - 96 = 59 is not).  Those groups take the shifted-vector kernel: two aligned 16-byte loads per
+// 16-byte store, the second one an L1 hit on the neighbour's first, re-assembled in registers.
+// Scalar fallback (row pitch or roi_w not a multiple of 4, unaligned base, or a window that reaches into the
 // reference's constant pad): plain predicated loads, 16-byte stores where the layout allows.
 #include <cuda.h>
 
@@ -206,6 +210,51 @@ __global__ void __launch_bounds__(256) extract_plain_kernel(const float* __restr
     }
 }
 
+// ---- shifted-vector path: aligned rows, window starts at any W offset ------------------------------
+// requires: all windows inside the volume, vext[2] % 4 == 0, roi_w % 4 == 0, 16-byte aligned bases
+// grid: x = 256-thread tiles over one (rh x rw/4) plane, y = groups of kShiftPlanes patch planes, z = (window, channel);
+// a thread copies the same quad of kShiftPlanes consecutive planes (independent loads, all in flight together)
+constexpr int kShiftPlanes = 8;
+
+__global__ void __launch_bounds__(256) extract_shifted_kernel(const float* __restrict__ vol, float* __restrict__ out,
+                                                              const ExtractParams p) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.centers != nullptr)
+        for (int w = threadIdx.x; w < p.n_windows; w += blockDim.x) write_centers(p, w);
+    const int rd = p.g.roi[0], rh = p.g.roi[1], rwq = p.g.roi[2] / 4;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= rh * rwq) return;
+    const int lh = idx / rwq, lq = idx - lh * rwq;
+    const int ld0 = blockIdx.y * kShiftPlanes;
+    const int w = blockIdx.z / p.n_channels, c = blockIdx.z - w * p.n_channels;
+    int b, id, ih, iw;
+    decode_window(p.g, p.first_window + w, b, id, ih, iw);  // uniform per block
+    const int vd = p.g.starts[0][id] + ld0 - p.vorg[0];
+    const int vh = p.g.starts[1][ih] + lh - p.vorg[1];
+    const int vw = p.g.starts[2][iw] + lq * 4 - p.vorg[2];
+    const int sh = vw & 3;  // uniform per window
+    const long long plane = static_cast<long long>(p.vext[1]) * p.vext[2];
+    const float* src = vol + (static_cast<long long>(b) * p.n_channels + c) * p.vext[0] * plane +
+                       static_cast<long long>(vd) * plane + static_cast<long long>(vh) * p.vext[2] + (vw - sh);
+    float* dst = out + ((static_cast<long long>(blockIdx.z) * rd + ld0) * rh + lh) * (rwq * 4) + lq * 4;
+    const long long dst_plane = static_cast<long long>(rh) * rwq * 4;
+    float4 a[kShiftPlanes], n[kShiftPlanes];
+#pragma unroll
+    for (int d = 0; d < kShiftPlanes; ++d)
+        if (ld0 + d < rd) {
+            a[d] = ld_stream_f4(src + d * plane);
+            if (sh != 0) n[d] = __ldg(reinterpret_cast<const float4*>(src + d * plane + 4));  // inside the padded row
+        }
+#pragma unroll
+    for (int d = 0; d < kShiftPlanes; ++d)
+        if (ld0 + d < rd) {
+            float4 v = a[d];
+            if (sh == 1) v = make_float4(a[d].y, a[d].z, a[d].w, n[d].x);
+            else if (sh == 2) v = make_float4(a[d].z, a[d].w, n[d].x, n[d].y);
+            else if (sh == 3) v = make_float4(a[d].w, n[d].x, n[d].y, n[d].z);
+            *reinterpret_cast<float4*>(dst + d * dst_plane) = v;
+        }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -276,9 +325,17 @@ extern "C" int mss_extract_patches(const float* volume, const int32_t vol_origin
     }
     cudaStream_t s = as_stream(stream);
     const int rw = p.g.roi[2];
-    const bool tma_ok = use_tma != 0 && inside && (vol_extent[2] % 4 == 0) && (rw % 4 == 0) && rw <= 256 &&
-                        (reinterpret_cast<uintptr_t>(volume) % 16 == 0) &&
-                        (reinterpret_cast<uintptr_t>(patches_out) % 16 == 0) && encode_tiled_fn() != nullptr;
+    // vector paths: all windows inside the volume, rows and patches 16-byte tiled
+    const bool vec_layout = inside && (vol_extent[2] % 4 == 0) && (rw % 4 == 0) &&
+                            (reinterpret_cast<uintptr_t>(volume) % 16 == 0) &&
+                            (reinterpret_cast<uintptr_t>(patches_out) % 16 == 0);
+    bool starts_aligned = true;  // TMA boxes must start on a 16-byte boundary of the innermost dimension
+    {
+        const int32_t* st = t + t[kHdrOffStarts + 2];
+        for (int i = lay->win_lo[2]; i < lay->win_hi[2]; ++i)
+            if ((st[i] - vol_origin[2]) % 4 != 0) starts_aligned = false;
+    }
+    const bool tma_ok = use_tma == 1 && vec_layout && starts_aligned && rw <= 256 && encode_tiled_fn() != nullptr;
     if (tma_ok) {
         CUtensorMap in_map, out_map;
         const long long in_dims[4] = {vol_extent[2], vol_extent[1], vol_extent[0],
@@ -308,6 +365,14 @@ extern "C" int mss_extract_patches(const float* volume, const int32_t vol_origin
         return MSS_OK;
     }
     const long long elems = static_cast<long long>(n_windows) * n_channels * p.g.roi[0] * p.g.roi[1] * rw;
+    if (vec_layout && use_tma != 2 && p.g.roi[0] <= 65535 && static_cast<long long>(n_windows) * n_channels <= 65535) {
+        dim3 grid(static_cast<unsigned>((p.g.roi[1] * (rw / 4) + 255) / 256),
+                  static_cast<unsigned>((p.g.roi[0] + kShiftPlanes - 1) / kShiftPlanes),
+                  static_cast<unsigned>(n_windows * n_channels));
+        extract_shifted_kernel<<<grid, 256, 0, s>>>(volume, patches_out, p);
+        MSS_CUDA(cudaGetLastError());
+        return MSS_OK;
+    }
     const bool vec = (rw % 4 == 0) && (reinterpret_cast<uintptr_t>(patches_out) % 16 == 0);
     const long long work = vec ? elems / 4 : elems;
     long long blocks = (work + 255) / 256;

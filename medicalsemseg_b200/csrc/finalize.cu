@@ -192,6 +192,72 @@ __global__ void __launch_bounds__(kFinThreads, MODE == kFinLabels ? 3 : 2) final
     }
 }
 
+// Labels only, few classes (K <= 4, e.g. BraTS' 3): a voxel carries so few bytes that a thread takes QPT quads of
+// the plane (a CTA-stride apart, so every load stays coalesced) and issues all QPT * K loads before the first compare.
+template <int K, int QPT>
+__global__ void __launch_bounds__(kFinThreads) finalize_labels_smallk_kernel(const __grid_constant__ FinParams p) {
+    const Geo& g = p.g;
+    const int ld = p.box_lo[0] + blockIdx.y;
+    const int b = blockIdx.z;
+    const int hi_w = min(p.box_lo[2] + p.box_n[2], g.ext[2]);
+    const long long plane = static_cast<long long>(g.ext[1]) * g.pitch;
+    const long long cstride = static_cast<long long>(g.ext[0]) * plane;
+    const long long base = static_cast<long long>(b) * K * cstride + static_cast<long long>(ld) * plane;
+    const int per_plane = p.nq * p.box_n[1];
+    float4 v[QPT][K];
+    int lh[QPT], lw[QPT];
+    bool in_box[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const int t = (blockIdx.x * QPT + q) * kFinThreads + threadIdx.x;
+        in_box[q] = t < per_plane;
+        const int row = in_box[q] ? t / p.nq : 0;
+        lh[q] = p.box_lo[1] + row;
+        lw[q] = p.box_lo[2] + (in_box[q] ? t - row * p.nq : 0) * 4;
+        in_box[q] = in_box[q] && lw[q] < hi_w;
+        const float* src = p.logits + base + static_cast<long long>(lh[q]) * g.pitch + lw[q];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (in_box[q]) v[q][k] = ld_stream_f4(src + k * cstride);
+    }
+    unsigned ties = 0;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        if (!in_box[q]) continue;
+        ArgmaxState am[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) am[e].reset();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            am[0].push(v[q][k].x, k);
+            am[1].push(v[q][k].y, k);
+            am[2].push(v[q][k].z, k);
+            am[3].push(v[q][k].w, k);
+        }
+        uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
+                       static_cast<long long>(lh[q]) * p.label_pitch + lw[q];
+        unsigned packed = 0;
+        const int nv = min(4, hi_w - lw[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (e < nv) {
+                packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
+                ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
+            }
+        if (nv == 4 && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
+            *reinterpret_cast<unsigned*>(lab) = packed;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < nv) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+        }
+    }
+    if (p.near_ties != nullptr) {
+        const unsigned warp_ties = __reduce_add_sync(0xffffffffu, ties);
+        if (warp_ties != 0u && (threadIdx.x & 31) == 0) atomicAdd(p.near_ties, static_cast<unsigned long long>(warp_ties));
+    }
+}
+
 template <int MODE>
 static void launch_fin(dim3 grid, cudaStream_t s, const FinParams& p) {
     if (p.g.K % 7 == 0)
@@ -248,7 +314,16 @@ extern "C" int mss_finalize_labels(const mss_layout_t* lay, const float* logits,
         launch_fin<kFinProbs>(grid, s, p);
     else if (logits_out != nullptr)
         launch_fin<kFinNormalise>(grid, s, p);
-    else
+    else if (g.K <= 4) {
+        constexpr int kQ = 4;
+        grid.x = static_cast<unsigned>((per_plane + kFinThreads * kQ - 1) / (kFinThreads * kQ));
+        switch (g.K) {
+            case 1: finalize_labels_smallk_kernel<1, kQ><<<grid, kFinThreads, 0, s>>>(p); break;
+            case 2: finalize_labels_smallk_kernel<2, kQ><<<grid, kFinThreads, 0, s>>>(p); break;
+            case 3: finalize_labels_smallk_kernel<3, kQ><<<grid, kFinThreads, 0, s>>>(p); break;
+            default: finalize_labels_smallk_kernel<4, kQ><<<grid, kFinThreads, 0, s>>>(p); break;
+        }
+    } else
         launch_fin<kFinLabels>(grid, s, p);  // labels only: the weight count cannot change the argmax
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;

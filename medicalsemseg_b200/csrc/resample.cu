@@ -1,0 +1,219 @@
+// Nearest-neighbour resampling of a uint8 label map back to the original grid
+// (replaces utils/misc.py:420-425 `resample_3d` = scipy.ndimage.zoom(order=0, prefilter=False), called at
+// engine/test.py:143-147 between the argmax and the NIfTI write that majority_vote.py consumes).
+//
+// scipy's zoom is separable: output index k of an axis reads input index floor(k * zoom + 0.5) with
+// zoom = (n_in - 1) / (n_out - 1) in float64 (1.0 when n_out == 1), and - mode 'constant' - answers cval = 0
+// when k * zoom falls outside [0, n_in - 1], which float rounding makes happen for the LAST index of some
+// (n_in, n_out) pairs.  mss_zoom_index_table reproduces that rule per axis on the host (-1 = constant);
+// the kernels are then pure byte gathers: out[x, y, z] = in[ix[x], iy[y], iz[z]].
+// Rows kernel: a CTA walks a range of output rows (b, x, y) in passes of `rp` rows.  A pass stages its source rows
+// in shared memory with aligned 16-byte copies, then every thread gathers the 16 voxels of its z-chunk from shared
+// memory (its 16 source indices live in registers for the whole kernel: the chunk of a thread never changes) and
+// stores them with one 16-byte store (4-byte / 1-byte stores where the output row is not 16-byte aligned).
+// Gather kernel: the general fallback (rows wider than 4096 voxels or too long for shared memory), byte loads via L1.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mss {
+
+struct ResampleParams {
+    const uint8_t* in;
+    uint8_t* out;
+    const int* ix;
+    const int* iy;
+    const int* iz;
+    int in_dims[3];
+    int out_dims[3];
+    long long n_volumes;
+    // rows kernel
+    int n_chunks;      // 16-voxel chunks per output row
+    int rp;            // rows per pass
+    int slot_pitch;    // bytes of one staged source row (multiple of 16)
+    int rows_per_block;
+};
+
+__device__ __forceinline__ void store_chunk(uint8_t* dst, const unsigned (&w)[4], int nz) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    if (nz == 16 && (a & 15u) == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if ((a & 3u) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * q + 4 <= nz) {
+                *reinterpret_cast<unsigned*>(dst + 4 * q) = w[q];
+            } else {
+                for (int e = 4 * q; e < nz; ++e) dst[e] = static_cast<uint8_t>(w[q] >> (8 * (e & 3)));
+            }
+        }
+    } else {
+        for (int e = 0; e < nz; ++e) dst[e] = static_cast<uint8_t>(w[e >> 2] >> (8 * (e & 3)));
+    }
+}
+
+__global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constant__ ResampleParams p) {
+    extern __shared__ __align__(16) uint8_t stage[];  // [rp][slot_pitch]
+    __shared__ int s_off[256];                        // per slot: byte offset of the row inside its slot, -1 = constant row
+    const int tid = threadIdx.x;
+    const int oz = p.out_dims[2], izd = p.in_dims[2];
+    const int chunk = tid % p.n_chunks, slot = tid / p.n_chunks;
+    const bool active = slot < p.rp;
+    const long long n_rows = p.n_volumes * p.out_dims[0] * p.out_dims[1];
+    const long long row_begin = static_cast<long long>(blockIdx.x) * p.rows_per_block;
+    const long long row_end = min(row_begin + p.rows_per_block, n_rows);
+    const int nz = min(16, oz - chunk * 16);
+    int zi[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) zi[e] = (active && e < nz) ? __ldg(p.iz + chunk * 16 + e) : -1;
+    const uint8_t* in_end = p.in + p.n_volumes * p.in_dims[0] * p.in_dims[1] * static_cast<long long>(izd);
+    const int nvec = p.slot_pitch / 16;
+
+    for (long long row0 = row_begin; row0 < row_end; row0 += p.rp) {
+        // ---- stage the source rows of this pass ------------------------------------------------------------
+        for (int v = tid; v < p.rp * nvec; v += 256) {
+            const int s = v / nvec, j = v - s * nvec;
+            const long long row = row0 + s;
+            if (row >= row_end) continue;
+            const int oy = static_cast<int>(row % p.out_dims[1]);
+            const long long r2 = row / p.out_dims[1];
+            const int ox = static_cast<int>(r2 % p.out_dims[0]);
+            const long long b = r2 / p.out_dims[0];
+            const int sx = __ldg(p.ix + ox), sy = __ldg(p.iy + oy);
+            if (sx < 0 || sy < 0) {
+                if (j == 0) s_off[s] = -1;
+                continue;
+            }
+            const uint8_t* src = p.in + ((b * p.in_dims[0] + sx) * p.in_dims[1] + sy) * static_cast<long long>(izd);
+            const int m = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+            if (j == 0) s_off[s] = m;
+            if (16 * j >= m + izd) continue;  // this vector lies behind the row
+            const uint8_t* g = src - m + 16 * j;
+            uint8_t* d = stage + static_cast<size_t>(s) * p.slot_pitch + 16 * j;
+            if (g >= p.in && g + 16 <= in_end) {
+                *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(g));
+            } else {
+                for (int e = 0; e < 16; ++e) d[e] = (g + e >= p.in && g + e < in_end) ? g[e] : 0;
+            }
+        }
+        __syncthreads();
+        // ---- gather -----------------------------------------------------------------------------------------
+        const long long row = row0 + slot;
+        if (active && row < row_end) {
+            const int off = s_off[slot];
+            const uint8_t* base = stage + static_cast<size_t>(slot) * p.slot_pitch + (off < 0 ? 0 : off);
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+            if (off >= 0) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const unsigned v = zi[e] >= 0 ? static_cast<unsigned>(base[zi[e]]) : 0u;
+                    w[e >> 2] |= v << (8 * (e & 3));
+                }
+            }
+            store_chunk(p.out + row * oz + chunk * 16, w, nz);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) resample_gather_kernel(const __grid_constant__ ResampleParams p) {
+    const int oz_chunks = (p.out_dims[2] + 15) / 16;
+    const long long rows = p.n_volumes * p.out_dims[0] * p.out_dims[1];
+    const long long total = rows * oz_chunks;
+    const long long in_plane = static_cast<long long>(p.in_dims[1]) * p.in_dims[2];
+    const long long in_vol = in_plane * p.in_dims[0];
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = t / oz_chunks;
+        const int z0 = static_cast<int>(t - row * oz_chunks) * 16;
+        const int oy = static_cast<int>(row % p.out_dims[1]);
+        const long long r2 = row / p.out_dims[1];
+        const int ox = static_cast<int>(r2 % p.out_dims[0]);
+        const long long b = r2 / p.out_dims[0];
+        const int sx = __ldg(p.ix + ox), sy = __ldg(p.iy + oy);
+        const bool row_in = sx >= 0 && sy >= 0;
+        const uint8_t* src = p.in + b * in_vol + static_cast<long long>(row_in ? sx : 0) * in_plane +
+                             static_cast<long long>(row_in ? sy : 0) * p.in_dims[2];
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        const int nz = min(16, p.out_dims[2] - z0);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            if (e < nz) {
+                const int sz = __ldg(p.iz + z0 + e);
+                const unsigned v = (row_in && sz >= 0) ? static_cast<unsigned>(__ldg(src + sz)) : 0u;
+                w[e >> 2] |= v << (8 * (e & 3));
+            }
+        }
+        store_chunk(p.out + row * p.out_dims[2] + z0, w, nz);
+    }
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" int mss_zoom_index_table(int32_t n_in, int32_t n_out, int32_t* table_out) {
+    MSS_REQUIRE(n_in > 0 && n_out > 0 && table_out != nullptr, MSS_E_ARG, "zoom_index_table: need positive sizes and a table");
+    // scipy.ndimage.zoom, grid_mode=False: zoom = (n_in - 1) / (n_out - 1), 1.0 where the divisor is 0
+    const double zoom = n_out > 1 ? static_cast<double>(n_in - 1) / static_cast<double>(n_out - 1) : 1.0;
+    for (int32_t k = 0; k < n_out; ++k) {
+        const double cc = static_cast<double>(k) * zoom;
+        if (cc < 0.0 || cc > static_cast<double>(n_in - 1)) {
+            table_out[k] = -1;  // mode='constant': outside the input -> cval (0)
+        } else {
+            int32_t i = static_cast<int32_t>(std::floor(cc + 0.5));  // order 0: nearest
+            table_out[k] = i > n_in - 1 ? n_in - 1 : i;
+        }
+    }
+    return MSS_OK;
+}
+
+extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_dims[3], uint8_t* labels_out,
+                                    const int32_t out_dims[3], int64_t n_volumes, const int32_t* index_x,
+                                    const int32_t* index_y, const int32_t* index_z, void* stream) {
+    MSS_REQUIRE(labels_in && in_dims && labels_out && out_dims && index_x && index_y && index_z, MSS_E_ARG,
+                "resample_nearest: null argument");
+    ResampleParams p;
+    for (int a = 0; a < 3; ++a) {
+        MSS_REQUIRE(in_dims[a] > 0 && out_dims[a] > 0, MSS_E_ARG, "resample_nearest: dims must be positive");
+        p.in_dims[a] = in_dims[a];
+        p.out_dims[a] = out_dims[a];
+    }
+    MSS_REQUIRE(n_volumes > 0, MSS_E_ARG, "resample_nearest: n_volumes must be positive");
+    p.in = labels_in;
+    p.out = labels_out;
+    p.ix = index_x;
+    p.iy = index_y;
+    p.iz = index_z;
+    p.n_volumes = n_volumes;
+    cudaStream_t s = as_stream(stream);
+    const long long n_rows = n_volumes * out_dims[0] * out_dims[1];
+    MSS_REQUIRE(n_rows < (1LL << 31), MSS_E_UNSUPPORTED, "resample_nearest: too many output rows for one call");
+    p.n_chunks = (out_dims[2] + 15) / 16;
+    p.slot_pitch = (in_dims[2] + 15 + 15) / 16 * 16;
+    constexpr int kMaxStage = 96 * 1024;
+    p.rp = p.n_chunks <= 256 ? 256 / p.n_chunks : 0;
+    if (p.rp > kMaxStage / p.slot_pitch) p.rp = kMaxStage / p.slot_pitch;
+    if (p.rp >= 1) {
+        // about 8 CTAs per SM's worth of row ranges, each a multiple of the pass size
+        long long per_block = (n_rows + 148LL * 8 - 1) / (148LL * 8);
+        per_block = (per_block + p.rp - 1) / p.rp * p.rp;
+        p.rows_per_block = static_cast<int>(per_block);
+        const long long blocks = (n_rows + per_block - 1) / per_block;
+        const size_t smem = static_cast<size_t>(p.rp) * p.slot_pitch;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MSS_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+            attr_set = true;
+        }
+        resample_rows_kernel<<<static_cast<unsigned>(blocks), 256, smem, s>>>(p);
+    } else {
+        p.rows_per_block = 0;
+        const long long total = n_rows * p.n_chunks;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        resample_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+    }
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}

@@ -188,7 +188,7 @@ class Stitcher:
         stream = torch.cuda.current_stream().cuda_stream
         with self.timer("extract"):
             rc = self.lib.mss_extract_patches(volume.data_ptr(), vorg, vext, cin, float(cval), C.byref(lay), first, n,
-                                              patches.data_ptr(), centers.data_ptr(), 1 if self.use_tma else 0, stream)
+                                              patches.data_ptr(), centers.data_ptr(), int(self.use_tma), stream)
         _lib.check(rc, "mss_extract_patches")
         if self.stats is not None:
             self.stats.gpu_launches += 1

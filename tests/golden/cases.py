@@ -56,3 +56,20 @@ def make_vote_maps(case: dict) -> list:
         noise = rs.randint(0, hi, size=case["shape"]).astype(np.uint8)
         maps.append(np.where(flip, noise, base).astype(np.uint8))
     return maps
+
+
+# label-map resampling after the argmax (utils/misc.py:420-425): seeded uint8 maps zoomed to a target grid.
+# (8, 12) -> (26, 86) are size pairs where scipy's coordinate overshoots and the last plane becomes 0.
+RESAMPLE_CASES = {
+    "up_quirk": dict(shape=[8, 12, 20], target=[26, 86, 20], k=14, seed=31),
+    "down": dict(shape=[40, 36, 31], target=[17, 36, 12], k=14, seed=32),
+    "mixed": dict(shape=[33, 20, 48], target=[50, 7, 61], k=3, seed=33),
+    "identity": dict(shape=[16, 16, 16], target=[16, 16, 16], k=5, seed=34),
+    "to_one": dict(shape=[9, 10, 11], target=[1, 10, 23], k=4, seed=35),
+    "spacing_like": dict(shape=[96, 96, 64], target=[128, 128, 43], k=14, seed=36),   # Spacingd round trip shape class
+}
+
+
+def make_label_map(case: dict) -> np.ndarray:
+    rs = np.random.RandomState(case["seed"])
+    return rs.randint(0, case["k"], size=case["shape"]).astype(np.uint8)

@@ -35,7 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "monai_shim"))
 sys.path.insert(0, REF)
 
 from oracle.predictors import ArithmeticPredictor  # noqa: E402
-from tests.golden.cases import SW_CASES, VOTE_CASES, make_volume, make_vote_maps  # noqa: E402
+from tests.golden.cases import (RESAMPLE_CASES, SW_CASES, VOTE_CASES, make_label_map, make_volume,  # noqa: E402
+                                make_vote_maps)
 
 
 def sha(a: np.ndarray) -> str:
@@ -51,11 +52,24 @@ def load_reference_vote():
     return ns["get_class_votes"], ns["get_new_label"]
 
 
+def load_reference_resample():
+    """utils/misc.py imports half the project at module level; its resample_3d (:420-425) is pure scipy and is
+    AST-extracted and executed unchanged."""
+    from scipy import ndimage
+
+    src = open(os.path.join(REF, "utils", "misc.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "resample_3d"]
+    ns = {"ndimage": ndimage, "np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "utils/misc.py", "exec"), ns)  # noqa: S102
+    return ns["resample_3d"]
+
+
 def main() -> None:
     torch.set_num_threads(os.cpu_count() or 1)
     from engine.utils import sliding_window_inference as ref_swi  # the reference itself
 
-    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}}
+    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}}
     for name, c in SW_CASES.items():
         vol = torch.from_numpy(make_volume(c))
         pred = ArithmeticPredictor(c["k"])
@@ -92,6 +106,15 @@ def main() -> None:
         np.savez_compressed(os.path.join(HERE, f"vote_{name}.npz"), voted=new, votes_sum=votes.sum(axis=(1, 2, 3)))
         manifest["vote"][name] = {"sha256": sha(new), "shape": list(new.shape)}
         print("vote", name, new.shape, sha(new)[:12])
+
+    ref_resample = load_reference_resample()
+    for name, c in RESAMPLE_CASES.items():
+        img = make_label_map(c)
+        out = ref_resample(img, c["target"])
+        np.savez_compressed(os.path.join(HERE, f"resample_{name}.npz"), out=out)
+        manifest["resample"][name] = {"sha256": sha(out), "shape": list(out.shape), "zero_planes_last": [
+            bool((np.take(out, -1, axis=a) == 0).all()) for a in range(3)]}
+        print("resample", name, out.shape, sha(out)[:12])
 
     # importance maps as the shimmed MONAI-0.8 restatement produces them (unpinned, recorded for drift detection)
     from oracle.monai08 import compute_importance_map

@@ -21,6 +21,7 @@ def extract_all(vol, roi, overlap, cval, use_tma, batch=3):
     plan = inferer.get_plan(tuple(vol.shape[2:]), roi, overlap, vol.device, vol.shape[0])
     imp = torch.ones(plan.grid.roi, device=vol.device)
     st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LOGITS, sw_batch=batch, use_tma=use_tma)
+    vol = inferer._tma_ready(vol, plan.grid, cval)  # as the inferer hands it over: W padded to a multiple of 4
     patches, centers = [], []
     for first in range(0, st.total, batch):
         n = min(batch, st.total - first)
@@ -37,8 +38,15 @@ def extract_all(vol, roi, overlap, cval, use_tma, batch=3):
     ((1, 2, 41, 37, 50), (24, 16, 32), 0.5, 0.0),  # W % 4 != 0: plain path
     ((1, 1, 10, 40, 21), 16, 0.25, -0.697),     # padded: plain path with cval
     ((1, 1, 30, 30, 30), (15, 10, 7), 0.3, 0.0),  # roi_w % 4 != 0
+    ((1, 2, 40, 36, 52), (16, 16, 32), 0.5, 0.0),  # W starts 0,16,20: all aligned
+    ((1, 2, 40, 36, 56), (16, 16, 24), 0.5, 0.0),  # W starts 0,12,24,32
+    ((1, 4, 48, 40, 155), (32, 32, 96), 0.5, 0.0),  # BraTS-like: W padded to 156, clamped start 59 -> shift 3
+    ((1, 1, 24, 20, 44), (16, 16, 16), 0.5, 0.0),  # W starts 0,8,16,24,28
+    ((1, 1, 24, 20, 88), (16, 16, 48), 0.3, 0.0),  # interval 33: W starts 0,33,40 -> shifts 1 and 0
+    ((1, 3, 20, 20, 60), (16, 16, 16), 0.6, 0.0),  # interval 6: shifts 0,2 and the clamped 44
+    ((1, 1, 20, 20, 64), (16, 16, 20), 0.45, 0.0),  # interval 11: every shift 0..3
 ])
-@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("use_tma", [1, 0, 2])
 def test_extract_matches_slicing(shape, roi, overlap, cval, use_tma):
     rs = np.random.RandomState(11)
     vol = torch.from_numpy(rs.standard_normal(shape).astype(np.float32)).cuda()
@@ -210,3 +218,29 @@ def test_extract_ahead_equals_per_batch():
     ref = got[per_window]
     for budget, (p, c) in got.items():
         assert torch.equal(p, ref[0]) and torch.equal(c, ref[1])
+
+
+from oracle import resample as oresample  # noqa: E402
+from tests.golden.cases import RESAMPLE_CASES, make_label_map  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(RESAMPLE_CASES))
+def test_resample_3d_bit_exact(name):
+    from medicalsemseg_b200.resample import resample_3d
+    case = RESAMPLE_CASES[name]
+    img = make_label_map(case)
+    got = resample_3d(torch.from_numpy(img).cuda(), case["target"]).cpu().numpy()
+    assert np.array_equal(got, np.load(os.path.join(GOLD, f"resample_{name}.npz"))["out"])
+    assert np.array_equal(got, oresample.resample_3d(img, case["target"]))
+
+
+def test_resample_3d_batched_and_large():
+    from medicalsemseg_b200.resample import resample_3d
+    rs = np.random.RandomState(77)
+    imgs = rs.randint(0, 14, (3, 37, 41, 29)).astype(np.uint8)
+    got = resample_3d(torch.from_numpy(imgs).cuda(), (64, 30, 48)).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], oresample.resample_3d(imgs[b], (64, 30, 48)))
+    big = rs.randint(0, 14, (200, 200, 96)).astype(np.uint8)   # BTCV-like: resampled grid back to the original one
+    got = resample_3d(torch.from_numpy(big).cuda(), (512, 512, 147)).cpu().numpy()
+    assert np.array_equal(got, oresample.resample_3d(big, (512, 512, 147)))

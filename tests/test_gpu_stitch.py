@@ -210,3 +210,57 @@ def test_slab_partition_emulated_ranks(name, world, axis):
         logits[tuple(lidx)] = slab._region(norm, ax, part.own_lo[r] - part.buf_lo[r], part.own_hi[r] - part.buf_lo[r])[..., :grid.image_size[2] if ax != 2 else None]
     assert rel_err(logits.cpu(), ref) <= TOL
     assert_labels_match(labels, ref)
+
+
+@pytest.mark.parametrize("name,world,dims", [("aniso_ragged", 4, (1, 2, 2)), ("basic_b1", 4, (2, 2, 1)),
+                                             ("overlap_075", 8, (2, 2, 2)), ("brats_like", 8, (2, 2, 2)),
+                                             ("overlap_075", 4, (1, 1, 4)), ("cfg1_geometry", 8, (2, 2, 2))])
+def test_block_partition_emulated_ranks(name, world, dims):
+    """The 3-D block partition (medicalsemseg_b200/block.py) rank after rank on one GPU: owned-window boxes cut along
+    several axes, raw accumulation, axis-by-axis halo reduction (device copies stand in for NCCL send/recv, same box
+    schedule as block.exchange_halos), finalise with the GLOBAL weight count."""
+    from medicalsemseg_b200 import block, slab
+    from medicalsemseg_b200.grid import make_grid
+    case = SW_CASES[name]
+    ref, _ = oracle_run(case, tuple_input=False)
+    vol, _ = cuda_inputs(case)
+    grid = make_grid(tuple(case["shape"][2:]), case["roi"], case["overlap"])
+    part = block.block_partition(grid, world, dims)
+    assert sum(part.n_windows(r) for r in range(world)) == grid.n_windows
+    sts = [block.local_pass(vol, ArithmeticPredictor(case["k"]), grid, part, r, case["mode"], sw_batch_size=case["sw_batch"],
+                            group_bytes=None if r % 2 else 1) for r in range(world)]
+    live_lo = {r: [0, 0, 0] for r in range(world)}
+    live_hi = {r: [h - l for l, h in zip(*part.box(r, "buf"))] for r in range(world)}
+    for a in (2, 1, 0):
+        p1 = part.axes[a]
+        for i in range(1, p1.world):  # ascending along the axis: a forwarding chain sees its predecessor's additions
+            for r in range(world):
+                c = list(part.coords(r))
+                if c[a] != i:
+                    continue
+                c[a] -= 1
+                prev = part.rank_of(c)
+                hlo, hhi = p1.halo(i - 1)
+                if hhi <= hlo:
+                    continue
+                blo, bhi = list(live_lo[r]), list(live_hi[r])
+                blo[a], bhi[a] = hlo - part.box(r, "buf")[0][a], hhi - part.box(r, "buf")[0][a]
+                plo, phi = list(live_lo[prev]), list(live_hi[prev])
+                plo[a], phi[a] = hlo - part.box(prev, "buf")[0][a], hhi - part.box(prev, "buf")[0][a]
+                src = block._box_view(sts[prev].acc, plo, phi).contiguous()
+                slab.cuda_halo_add(block._box_view(sts[r].acc, blo, bhi), src)
+        for r in range(world):
+            (bl, _), (ol, oh) = part.box(r, "buf"), part.box(r, "own")
+            live_lo[r][a], live_hi[r][a] = ol[a] - bl[a], oh[a] - bl[a]
+    labels = torch.empty((case["shape"][0],) + grid.image_size, dtype=torch.uint8, device="cuda")
+    logits = torch.empty((case["shape"][0], case["k"]) + grid.image_size, device="cuda")
+    for r in range(world):
+        norm = torch.empty_like(sts[r].acc)
+        own = block.finalize_owned(sts[r], part, r, logits_out=norm)
+        ol, oh = part.box(r, "own")
+        bl, _ = part.box(r, "buf")
+        block._box_view(labels, ol, oh).copy_(own)
+        block._box_view(logits, ol, oh).copy_(block._box_view(norm, [ol[x] - bl[x] for x in range(3)],
+                                                              [oh[x] - bl[x] for x in range(3)]))
+    assert rel_err(logits.cpu(), ref) <= TOL
+    assert_labels_match(labels, ref)

@@ -65,3 +65,34 @@ def test_vote_matches_reference_run(name):
     votes = ovote.class_votes(maps, case["k"])
     assert np.array_equal(fx["votes_sum"], votes.sum(axis=(1, 2, 3)))
     assert np.all(votes[0] == 1)
+
+
+from oracle import resample as oresample  # noqa: E402
+from tests.golden.cases import RESAMPLE_CASES, make_label_map  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(RESAMPLE_CASES))
+def test_resample_matches_reference_run(name):
+    """oracle.resample (scipy call and the index rule the kernel implements) vs outputs of the reference's own
+    resample_3d (utils/misc.py:420-425, AST-extracted and run by make_golden.py)."""
+    case = RESAMPLE_CASES[name]
+    img = make_label_map(case)
+    fx = np.load(os.path.join(GOLD, f"resample_{name}.npz"))["out"]
+    assert sha(fx) == MANIFEST["resample"][name]["sha256"]
+    assert np.array_equal(oresample.resample_3d(img, case["target"]), fx)
+    assert np.array_equal(oresample.resample_3d_rule(img, case["target"]), fx)
+
+
+def test_resample_quirk_is_pinned():
+    # scipy's coordinate overshoot zeroes the last plane for (8 -> 26) and (12 -> 86): the reference does this too
+    assert MANIFEST["resample"]["up_quirk"]["zero_planes_last"][:2] == [True, True]
+    assert oresample.zoom_index_rule(8, 26)[-1] == -1 and oresample.zoom_index_rule(12, 86)[-1] == -1
+    assert oresample.zoom_index_rule(20, 20)[-1] == 19
+
+
+def test_zoom_index_table_host_matches_rule():
+    from medicalsemseg_b200.resample import zoom_index_table, zoomed_shape
+    for n_in in list(range(1, 40)) + [96, 155, 200, 512]:
+        for n_out in list(range(1, 60)) + [155, 240, 333, 1024]:
+            assert np.array_equal(zoom_index_table(n_in, n_out), oresample.zoom_index_rule(n_in, n_out)), (n_in, n_out)
+    assert zoomed_shape((8, 12, 20), (26, 86, 20)) == (26, 86, 20)
