@@ -185,6 +185,16 @@ def main():
             med, mn = timed(lambda: resample_3d(lab, tgt), args.reps, flush)
             report(f"resample_3d -> {tgt[0]}x{tgt[1]}x{tgt[2]}", v + vo, med, mn, "uint8 gather: V_in + V_out bytes")
 
+    if want("intensity"):
+        from medicalsemseg_b200 import transforms as T
+        ct = torch.randn(cfg["shape"], device=dev) * 700 - 200
+        outb = torch.empty_like(ct)
+        med, mn = timed(lambda: T.scale_intensity_range(ct, -1000, 1000, 0.0, 1.0, True, out=outb), args.reps, flush)
+        report("intensity: range scale + clip", 8 * ct.numel(), med, mn)
+        med, mn = timed(lambda: T.scale_intensity_range(ct, -1000, 1000, 0.0, 1.0, True, cubed=True, float64=True, out=outb),
+                        args.reps, flush)
+        report("intensity: cubed scaler (f64 chain)", 8 * ct.numel(), med, mn)
+
     if want("halo"):
         rows, length = k * 512, 512 * 48
         a = torch.randn(rows, length, device=dev)

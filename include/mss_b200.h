@@ -187,6 +187,26 @@ int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_dims[3], uin
                          const int32_t out_dims[3], int64_t n_volumes, const int32_t* index_x,
                          const int32_t* index_y, const int32_t* index_z, void* stream);
 
+/* ---- before the sliding window: test-time intensity transforms -------- */
+
+#define MSS_INT_CBRT 1     /* x = cbrt(x)                          data/transforms.py:54 (ScaleCubedIntensityRange) */
+#define MSS_INT_SCALE 2    /* x = (x - a_min) / (a_max - a_min)    data/transforms.py:62 / MONAI ScaleIntensityRange */
+#define MSS_INT_RESCALE 4  /* x = x * (b_max - b_min) + b_min      data/transforms.py:63-64                          */
+#define MSS_INT_CLIP_LO 8  /* x = max(x, b_min)                    data/transforms.py:65-66                          */
+#define MSS_INT_CLIP_HI 16 /* x = min(x, b_max)                                                                      */
+#define MSS_INT_NORM 32    /* x = (x - subtrahend) / divisor       MONAI NormalizeIntensity, data/dataset_builder.py:352-368 */
+#define MSS_INT_NONZERO 64 /* ... only where x != 0 (nonzero=True)                                                   */
+#define MSS_INT_F64 128    /* evaluate in float64, round to float32 once (NumPy >= 2 with float64 scalar bounds)     */
+
+/* The chain data/dataset_builder.py:322-370 applies to the test volume, fused into one elementwise pass over
+ * n float32 voxels (in may equal out).  Steps are applied in the order of the flag values above, each as a
+ * separately rounded operation of the working type (float32; float64 with MSS_INT_F64).  a_max_minus_a_min is
+ * (a_max - a_min) as the host language computed it (Python: a float64 difference); constants are rounded to the
+ * working type once. */
+int mss_intensity_transform(const float* in, float* out, int64_t n, int32_t flags, double a_min,
+                            double a_max_minus_a_min, double b_min, double b_max, double subtrahend, double divisor,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ MSS_F32, MSS_F16, MSS_BF16 = 0, 1, 2
 BLEND_CONSTANT, BLEND_PROFILES = 0, 1
 GAUSS_MONAI08_ERF, GAUSS_MONAI12_EXP = 0, 1
 FUSE_NONE, FUSE_LOGITS, FUSE_LABELS = 0, 1, 2
+INT_CBRT, INT_SCALE, INT_RESCALE, INT_CLIP_LO, INT_CLIP_HI, INT_NORM, INT_NONZERO, INT_F64 = 1, 2, 4, 8, 16, 32, 64, 128
 MAX_BATCH_PTRS = 128
 MAX_VOTE_MAPS = 15
 MAX_VOTE_CLASSES = 16
@@ -54,6 +55,8 @@ _SIGNATURES = {
     "mss_halo_add": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
     "mss_zoom_index_table": (C.c_int, [c_i32, c_i32, vp]),
     "mss_resample_nearest": (C.c_int, [vp, I3, vp, I3, c_i64, vp, vp, vp, vp]),
+    "mss_intensity_transform": (C.c_int, [vp, vp, c_i64, c_i32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_double, C.c_double, vp]),
 }
 
 EXPORTED = tuple(sorted(_SIGNATURES))

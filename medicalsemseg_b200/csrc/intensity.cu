@@ -1,0 +1,120 @@
+// Test-time intensity transforms of the volume, one fused elementwise pass
+// (replaces the chain built by data/dataset_builder.py:322-370: ScaleIntensityRange / ScaleCubedIntensityRange
+// (data/transforms.py:17-71) followed by NormalizeIntensity - the step right before the sliding window,
+// SURVEY.md section 8f rank 2).
+//
+//   [x = cbrt(x)]                                     MSS_INT_CBRT      data/transforms.py:54
+//   [x = (x - a_min) / (a_max - a_min)]               MSS_INT_SCALE     data/transforms.py:62
+//   [x = x * (b_max - b_min) + b_min]                 MSS_INT_RESCALE   data/transforms.py:63-64
+//   [x = clip(x, b_min, b_max)]                       MSS_INT_CLIP_LO / _HI   data/transforms.py:65-66
+//   [x = (x - sub) / div  (only where x != 0)]        MSS_INT_NORM (+ MSS_INT_NONZERO)   MONAI NormalizeIntensity
+// Every step is a separately rounded operation (sub, div, mul, add; no FMA contraction) in the order the NumPy /
+// torch expression evaluates it - in float32, or with MSS_INT_F64 in float64 rounded to float32 once at the end,
+// which is what NumPy >= 2 does to the reference's cubed scaler (it subtracts the float64 scalar np.cbrt(a_min) from
+// a float32 array).  The fixed-range and normalise paths are bit-identical to NumPy; cbrtf differs from glibc's by
+// at most 1 ulp.  8 bytes of traffic per voxel, 16-byte accesses.
+#include "common.cuh"
+
+namespace mss {
+
+struct IntensityParams {
+    int flags;
+    double a_min, denom, b_scale, b_min, b_max, sub, div;
+};
+
+template <typename T>
+struct Arith;
+template <>
+struct Arith<float> {
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <>
+struct Arith<double> {
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+
+template <typename T>
+__device__ __forceinline__ float intensity_one(float x0, const IntensityParams& p) {
+    using A = Arith<T>;
+    if (p.flags & MSS_INT_CBRT) x0 = cbrtf(x0);  // np.cbrt of a float32 array stays float32
+    T x = static_cast<T>(x0);
+    if (p.flags & MSS_INT_SCALE) x = A::div(A::sub(x, static_cast<T>(p.a_min)), static_cast<T>(p.denom));
+    if (p.flags & MSS_INT_RESCALE) x = A::add(A::mul(x, static_cast<T>(p.b_scale)), static_cast<T>(p.b_min));
+    if (p.flags & MSS_INT_CLIP_LO) x = (x < static_cast<T>(p.b_min)) ? static_cast<T>(p.b_min) : x;  // NaN stays NaN
+    if (p.flags & MSS_INT_CLIP_HI) x = (x > static_cast<T>(p.b_max)) ? static_cast<T>(p.b_max) : x;
+    if (p.flags & MSS_INT_NORM) {
+        if (!(p.flags & MSS_INT_NONZERO) || x != static_cast<T>(0))
+            x = A::div(A::sub(x, static_cast<T>(p.sub)), static_cast<T>(p.div));
+    }
+    return static_cast<float>(x);
+}
+
+template <bool VEC, typename T>
+__global__ void __launch_bounds__(256) intensity_kernel(const float* __restrict__ in, float* __restrict__ out, long long n,
+                                                        const IntensityParams p) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long n4 = VEC ? n / 4 : 0;
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (long long i = tid; i < n4; i += stride * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < n4) v[u] = ld_stream_f4(in + (i + u * stride) * 4);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < n4) {
+                float4 r;
+                r.x = intensity_one<T>(v[u].x, p);
+                r.y = intensity_one<T>(v[u].y, p);
+                r.z = intensity_one<T>(v[u].z, p);
+                r.w = intensity_one<T>(v[u].w, p);
+                *reinterpret_cast<float4*>(out + (i + u * stride) * 4) = r;
+            }
+    }
+    for (long long i = n4 * 4 + tid; i < n; i += stride) out[i] = intensity_one<T>(in[i], p);
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" int mss_intensity_transform(const float* in, float* out, int64_t n, int32_t flags, double a_min,
+                                       double a_max_minus_a_min, double b_min, double b_max, double subtrahend, double divisor,
+                                       void* stream) {
+    MSS_REQUIRE(in != nullptr && out != nullptr && n > 0, MSS_E_ARG, "intensity_transform: null argument or empty volume");
+    MSS_REQUIRE((flags & ~0xff) == 0, MSS_E_ARG, "intensity_transform: unknown flag bits 0x%x", flags);
+    IntensityParams p;
+    p.flags = flags;
+    const bool f64 = (flags & MSS_INT_F64) != 0;
+    p.a_min = a_min;
+    p.denom = a_max_minus_a_min;
+    p.b_min = b_min;
+    p.b_max = b_max;
+    // (b_max - b_min) as the host expression computes it: float64 difference (Python floats), rounded to the working type
+    p.b_scale = b_max - b_min;
+    p.sub = subtrahend;
+    p.div = divisor;
+    if (!f64) {  // float32 arithmetic: constants are rounded to float32 once, like NumPy does with Python scalars
+        p.a_min = static_cast<float>(p.a_min), p.denom = static_cast<float>(p.denom), p.b_min = static_cast<float>(p.b_min);
+        p.b_max = static_cast<float>(p.b_max), p.b_scale = static_cast<float>(p.b_scale);
+        p.sub = static_cast<float>(p.sub), p.div = static_cast<float>(p.div);
+    }
+    const bool vec = reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    long long blocks = (n / 16 + 255) / 256 + 1;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    const unsigned nb = static_cast<unsigned>(blocks);
+    cudaStream_t s = as_stream(stream);
+    if (vec && f64) intensity_kernel<true, double><<<nb, 256, 0, s>>>(in, out, n, p);
+    else if (vec) intensity_kernel<true, float><<<nb, 256, 0, s>>>(in, out, n, p);
+    else if (f64) intensity_kernel<false, double><<<nb, 256, 0, s>>>(in, out, n, p);
+    else intensity_kernel<false, float><<<nb, 256, 0, s>>>(in, out, n, p);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}

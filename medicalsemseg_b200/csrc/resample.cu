@@ -34,57 +34,70 @@ struct ResampleParams {
     int rows_per_block;
 };
 
+// 16 gathered voxels (little-endian in w) -> dst, with the widest stores the address allows
 __device__ __forceinline__ void store_chunk(uint8_t* dst, const unsigned (&w)[4], int nz) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-    if (nz == 16 && (a & 15u) == 0) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else if ((a & 3u) == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (4 * q + 4 <= nz) {
-                *reinterpret_cast<unsigned*>(dst + 4 * q) = w[q];
-            } else {
-                for (int e = 4 * q; e < nz; ++e) dst[e] = static_cast<uint8_t>(w[q] >> (8 * (e & 3)));
-            }
+    const unsigned a = static_cast<unsigned>(reinterpret_cast<uintptr_t>(dst));
+    if (nz == 16) {
+        if ((a & 15u) == 0) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            return;
         }
-    } else {
-        for (int e = 0; e < nz; ++e) dst[e] = static_cast<uint8_t>(w[e >> 2] >> (8 * (e & 3)));
+        const unsigned m = a & 3u;
+        if (m == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<unsigned*>(dst + 4 * q) = w[q];
+            return;
+        }
+        // head bytes up to the next 4-byte boundary, three aligned words built by funnel shifts, tail bytes
+        const unsigned head = 4u - m;
+        for (unsigned e = 0; e < head; ++e) dst[e] = static_cast<uint8_t>(w[0] >> (8 * e));
+        const unsigned sh = 8u * head;
+        *reinterpret_cast<unsigned*>(dst + head) = __funnelshift_r(w[0], w[1], sh);
+        *reinterpret_cast<unsigned*>(dst + head + 4) = __funnelshift_r(w[1], w[2], sh);
+        *reinterpret_cast<unsigned*>(dst + head + 8) = __funnelshift_r(w[2], w[3], sh);
+        for (unsigned e = 0; e < m; ++e) dst[head + 12 + e] = static_cast<uint8_t>(w[3] >> (sh + 8 * e));
+        return;
+    }
+    for (int e = 0; e < nz; ++e) {
+        const unsigned word = e < 4 ? w[0] : (e < 8 ? w[1] : (e < 12 ? w[2] : w[3]));
+        dst[e] = static_cast<uint8_t>(word >> (8 * (e & 3)));
     }
 }
 
+constexpr int kRowsPerThread = 4;  // rows a thread gathers per pass (same z-chunk, rows `rp` apart)
+
 __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constant__ ResampleParams p) {
-    extern __shared__ __align__(16) uint8_t stage[];  // [rp][slot_pitch]
-    __shared__ int s_off[256];                        // per slot: byte offset of the row inside its slot, -1 = constant row
+    extern __shared__ __align__(16) uint8_t stage[];  // [rp * kRowsPerThread][slot_pitch]
+    __shared__ int s_off[256 * kRowsPerThread];       // per slot: byte offset of the row inside its slot, -1 = constant row
     const int tid = threadIdx.x;
-    const int oz = p.out_dims[2], izd = p.in_dims[2];
+    const int oz = p.out_dims[2], izd = p.in_dims[2], oyd = p.out_dims[1], oxd = p.out_dims[0];
     const int chunk = tid % p.n_chunks, slot = tid / p.n_chunks;
     const bool active = slot < p.rp;
-    const long long n_rows = p.n_volumes * p.out_dims[0] * p.out_dims[1];
-    const long long row_begin = static_cast<long long>(blockIdx.x) * p.rows_per_block;
-    const long long row_end = min(row_begin + p.rows_per_block, n_rows);
+    const int n_rows = static_cast<int>(p.n_volumes) * oxd * oyd;  // < 2^31 (checked by the host)
+    const int row_begin = blockIdx.x * p.rows_per_block;
+    const int row_end = min(row_begin + p.rows_per_block, n_rows);
     const int nz = min(16, oz - chunk * 16);
     int zi[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) zi[e] = (active && e < nz) ? __ldg(p.iz + chunk * 16 + e) : -1;
     const uint8_t* in_end = p.in + p.n_volumes * p.in_dims[0] * p.in_dims[1] * static_cast<long long>(izd);
     const int nvec = p.slot_pitch / 16;
+    const int pass_rows = p.rp * kRowsPerThread;
 
-    for (long long row0 = row_begin; row0 < row_end; row0 += p.rp) {
+    for (int row0 = row_begin; row0 < row_end; row0 += pass_rows) {
         // ---- stage the source rows of this pass ------------------------------------------------------------
-        for (int v = tid; v < p.rp * nvec; v += 256) {
+        for (int v = tid; v < pass_rows * nvec; v += 256) {
             const int s = v / nvec, j = v - s * nvec;
-            const long long row = row0 + s;
+            const int row = row0 + s;
             if (row >= row_end) continue;
-            const int oy = static_cast<int>(row % p.out_dims[1]);
-            const long long r2 = row / p.out_dims[1];
-            const int ox = static_cast<int>(r2 % p.out_dims[0]);
-            const long long b = r2 / p.out_dims[0];
+            const int r2 = row / oyd, oy = row - r2 * oyd;
+            const int b = r2 / oxd, ox = r2 - b * oxd;
             const int sx = __ldg(p.ix + ox), sy = __ldg(p.iy + oy);
             if (sx < 0 || sy < 0) {
                 if (j == 0) s_off[s] = -1;
                 continue;
             }
-            const uint8_t* src = p.in + ((b * p.in_dims[0] + sx) * p.in_dims[1] + sy) * static_cast<long long>(izd);
+            const uint8_t* src = p.in + ((static_cast<long long>(b) * p.in_dims[0] + sx) * p.in_dims[1] + sy) * izd;
             const int m = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
             if (j == 0) s_off[s] = m;
             if (16 * j >= m + izd) continue;  // this vector lies behind the row
@@ -98,19 +111,24 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
         }
         __syncthreads();
         // ---- gather -----------------------------------------------------------------------------------------
-        const long long row = row0 + slot;
-        if (active && row < row_end) {
-            const int off = s_off[slot];
-            const uint8_t* base = stage + static_cast<size_t>(slot) * p.slot_pitch + (off < 0 ? 0 : off);
-            unsigned w[4] = {0u, 0u, 0u, 0u};
-            if (off >= 0) {
+        if (active) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const unsigned v = zi[e] >= 0 ? static_cast<unsigned>(base[zi[e]]) : 0u;
-                    w[e >> 2] |= v << (8 * (e & 3));
+            for (int rr = 0; rr < kRowsPerThread; ++rr) {
+                const int s = slot + rr * p.rp;
+                const int row = row0 + s;
+                if (row >= row_end) break;
+                const int off = s_off[s];
+                const uint8_t* base = stage + static_cast<size_t>(s) * p.slot_pitch + (off < 0 ? 0 : off);
+                unsigned w[4] = {0u, 0u, 0u, 0u};
+                if (off >= 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const unsigned v = zi[e] >= 0 ? static_cast<unsigned>(base[zi[e]]) : 0u;
+                        w[e >> 2] |= v << (8 * (e & 3));
+                    }
                 }
+                store_chunk(p.out + static_cast<long long>(row) * oz + chunk * 16, w, nz);
             }
-            store_chunk(p.out + row * oz + chunk * 16, w, nz);
         }
         __syncthreads();
     }
@@ -193,14 +211,15 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
     p.slot_pitch = (in_dims[2] + 15 + 15) / 16 * 16;
     constexpr int kMaxStage = 96 * 1024;
     p.rp = p.n_chunks <= 256 ? 256 / p.n_chunks : 0;
-    if (p.rp > kMaxStage / p.slot_pitch) p.rp = kMaxStage / p.slot_pitch;
+    if (p.rp > kMaxStage / (p.slot_pitch * kRowsPerThread)) p.rp = kMaxStage / (p.slot_pitch * kRowsPerThread);
     if (p.rp >= 1) {
-        // about 8 CTAs per SM's worth of row ranges, each a multiple of the pass size
-        long long per_block = (n_rows + 148LL * 8 - 1) / (148LL * 8);
-        per_block = (per_block + p.rp - 1) / p.rp * p.rp;
+        // about 4 CTAs per SM's worth of row ranges, each a multiple of the pass size
+        long long per_block = (n_rows + 148LL * 4 - 1) / (148LL * 4);
+        const int pass_rows = p.rp * kRowsPerThread;
+        per_block = (per_block + pass_rows - 1) / pass_rows * pass_rows;
         p.rows_per_block = static_cast<int>(per_block);
         const long long blocks = (n_rows + per_block - 1) / per_block;
-        const size_t smem = static_cast<size_t>(p.rp) * p.slot_pitch;
+        const size_t smem = static_cast<size_t>(pass_rows) * p.slot_pitch;
         static bool attr_set = false;
         if (!attr_set) {
             MSS_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));

@@ -73,3 +73,18 @@ RESAMPLE_CASES = {
 def make_label_map(case: dict) -> np.ndarray:
     rs = np.random.RandomState(case["seed"])
     return rs.randint(0, case["k"], size=case["shape"]).astype(np.uint8)
+
+
+# test-time intensity transform (the reference's own ScaleCubedIntensityRange, data/transforms.py:17-71, configured as at
+# data/dataset_builder.py:333-341): seeded CT-like volumes in Hounsfield units
+INTENSITY_CASES = {
+    "ct_default": dict(shape=[1, 24, 20, 28], a_min=-1000, a_max=1000, b_min=0.0, b_max=1.0, clip=True, seed=41),
+    "ct_soft": dict(shape=[1, 16, 16, 33], a_min=-175, a_max=250, b_min=0.0, b_max=1.0, clip=True, seed=42),
+    "noclip": dict(shape=[2, 9, 10, 11], a_min=-500, a_max=1500, b_min=-1.0, b_max=1.0, clip=False, seed=43),
+    "no_b": dict(shape=[1, 8, 8, 8], a_min=-1000, a_max=1000, b_min=None, b_max=None, clip=False, seed=44),
+}
+
+
+def make_ct_volume(case: dict) -> np.ndarray:
+    rs = np.random.RandomState(case["seed"])
+    return (rs.standard_normal(case["shape"]) * 700.0 - 200.0).astype(np.float32)

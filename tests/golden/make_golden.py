@@ -35,8 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "monai_shim"))
 sys.path.insert(0, REF)
 
 from oracle.predictors import ArithmeticPredictor  # noqa: E402
-from tests.golden.cases import (RESAMPLE_CASES, SW_CASES, VOTE_CASES, make_label_map, make_volume,  # noqa: E402
-                                make_vote_maps)
+from tests.golden.cases import (INTENSITY_CASES, RESAMPLE_CASES, SW_CASES, VOTE_CASES, make_ct_volume,  # noqa: E402
+                                make_label_map, make_volume, make_vote_maps)
 
 
 def sha(a: np.ndarray) -> str:
@@ -65,11 +65,33 @@ def load_reference_resample():
     return ns["resample_3d"]
 
 
+def load_reference_cubed_scaler():
+    """data/transforms.py imports MONAI at module level (absent here); the class ScaleCubedIntensityRange (:17-71) only
+    needs a base class, a clip and a dtype cast from it.  It is AST-extracted and executed unchanged with minimal
+    stand-ins for those three names (np.clip and ndarray.astype are what MONAI's helpers do for NumPy inputs)."""
+    from typing import Optional
+    from warnings import warn
+
+    src = open(os.path.join(REF, "data", "transforms.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ScaleCubedIntensityRange"]
+
+    class _Backends:
+        TORCH, NUMPY = "torch", "numpy"
+
+    ns = {"np": np, "Optional": Optional, "warn": warn, "Transform": object, "TransformBackends": _Backends,
+          "DtypeLike": object, "NdarrayOrTensor": object,
+          "clip": lambda a, lo, hi: np.clip(a, lo, hi),
+          "convert_data_type": lambda img, dtype=None: (np.asarray(img).astype(dtype), None, None)}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "data/transforms.py", "exec"), ns)  # noqa: S102
+    return ns["ScaleCubedIntensityRange"]
+
+
 def main() -> None:
     torch.set_num_threads(os.cpu_count() or 1)
     from engine.utils import sliding_window_inference as ref_swi  # the reference itself
 
-    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}}
+    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}, "intensity": {}}
     for name, c in SW_CASES.items():
         vol = torch.from_numpy(make_volume(c))
         pred = ArithmeticPredictor(c["k"])
@@ -115,6 +137,15 @@ def main() -> None:
         manifest["resample"][name] = {"sha256": sha(out), "shape": list(out.shape), "zero_planes_last": [
             bool((np.take(out, -1, axis=a) == 0).all()) for a in range(3)]}
         print("resample", name, out.shape, sha(out)[:12])
+
+    scaler_cls = load_reference_cubed_scaler()
+    for name, c in INTENSITY_CASES.items():
+        vol = make_ct_volume(c)
+        out = scaler_cls(c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"])(vol)
+        np.savez_compressed(os.path.join(HERE, f"intensity_{name}.npz"), out=out)
+        manifest["intensity"][name] = {"sha256": sha(out), "dtype": str(out.dtype), "numpy": np.__version__,
+                                       "min": float(out.min()), "max": float(out.max())}
+        print("intensity", name, out.shape, out.dtype, sha(out)[:12])
 
     # importance maps as the shimmed MONAI-0.8 restatement produces them (unpinned, recorded for drift detection)
     from oracle.monai08 import compute_importance_map

@@ -244,3 +244,80 @@ def test_resample_3d_batched_and_large():
     big = rs.randint(0, 14, (200, 200, 96)).astype(np.uint8)   # BTCV-like: resampled grid back to the original one
     got = resample_3d(torch.from_numpy(big).cuda(), (512, 512, 147)).cpu().numpy()
     assert np.array_equal(got, oresample.resample_3d(big, (512, 512, 147)))
+
+
+from oracle import transforms as otransforms  # noqa: E402
+from tests.golden.cases import INTENSITY_CASES, make_ct_volume  # noqa: E402
+
+
+def _ulp_close(got, want, ulps=1):
+    got, want = np.asarray(got, np.float32), np.asarray(want, np.float32)
+    tol = ulps * np.spacing(np.maximum(np.abs(want), np.float32(1e-30)).astype(np.float32))
+    return bool(np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol))
+
+
+@pytest.mark.parametrize("name", sorted(INTENSITY_CASES))
+def test_cubed_intensity_scaler_vs_reference_fixture(name):
+    from medicalsemseg_b200 import transforms as T
+    c = INTENSITY_CASES[name]
+    fx = np.load(os.path.join(GOLD, f"intensity_{name}.npz"))["out"]
+    vol = torch.from_numpy(make_ct_volume(c)).cuda()
+    got = T.scale_intensity_range(vol, c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"], cubed=True,
+                                  float64=True).cpu().numpy()
+    # float64 intermediates like the reference under NumPy >= 2; cbrtf (CUDA) vs cbrtf (glibc) may differ by 1 ulp
+    assert _ulp_close(got, fx, ulps=2)
+    assert np.mean(got == fx) > 0.9
+    got32 = T.scale_intensity_range(vol, c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"], cubed=True,
+                                    float64=False).cpu().numpy()
+    assert np.max(np.abs(got32 - fx)) <= 3e-7 * max(1.0, float(np.abs(fx).max()))
+
+
+@pytest.mark.parametrize("a_min,a_max,b_min,b_max,clip", [(-1000, 1000, 0.0, 1.0, True), (-175, 250, 0.0, 1.0, True),
+                                                          (-500, 1500, -1.0, 1.0, False), (0, 1, None, None, False),
+                                                          (5, 5, 0.5, 1.0, True), (-1000, 1000, None, 1.0, True)])
+def test_fixed_range_scaler_and_normalise_bit_exact(a_min, a_max, b_min, b_max, clip):
+    from medicalsemseg_b200 import transforms as T
+    rs = np.random.RandomState(3)
+    vol = (rs.standard_normal((2, 11, 13, 17)) * 700 - 200).astype(np.float32)
+    vol[0, 0, 0, :5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
+    want = otransforms.scale_intensity_range(vol, a_min, a_max, b_min, b_max, clip)
+    got = T.scale_intensity_range(torch.from_numpy(vol).cuda(), a_min, a_max, b_min, b_max, clip).cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True)
+    want_n = otransforms.normalize_intensity(want, 0.1943, 0.2786)
+    got_n = T.normalize_intensity(torch.from_numpy(want).cuda(), 0.1943, 0.2786).cpu().numpy()
+    assert np.array_equal(got_n, want_n, equal_nan=True)
+
+
+def test_statistics_based_intensity_transforms():
+    from medicalsemseg_b200 import transforms as T
+    rs = np.random.RandomState(4)
+    vol = (rs.standard_normal((2, 16, 18, 20)) * 300).astype(np.float32)
+    vol[rs.random_sample(vol.shape) < 0.3] = 0.0
+    dv = torch.from_numpy(vol).cuda()
+    got = T.normalize_intensity(dv, nonzero=True, channel_wise=True).cpu().numpy()
+    want = otransforms.normalize_intensity(vol, nonzero=True, channel_wise=True)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5) and np.array_equal(got == 0, want == 0)
+    for q in (5, 50, 95, 99.5):
+        assert T.percentile(dv, q) == pytest.approx(float(np.percentile(vol, q)), rel=1e-6, abs=1e-6)
+    got = T.scale_intensity_range_percentiles(dv, 5, 95, 0.0, 1.0, clip=True).cpu().numpy()
+    want = otransforms.scale_intensity_range_percentiles(vol, 5, 95, 0.0, 1.0, clip=True)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_test_time_intensity_chain_is_one_launch_equivalent():
+    from types import SimpleNamespace
+    from medicalsemseg_b200 import transforms as T
+    rs = np.random.RandomState(5)
+    vol = (rs.standard_normal((1, 20, 20, 24)) * 700 - 200).astype(np.float32)
+    dv = torch.from_numpy(vol).cuda()
+    cfg = SimpleNamespace(t_fixed_ct_intensity=True, t_ct_min=-1000, t_ct_max=1000, t_normalize=True, t_norm_mean=0.1943,
+                          t_norm_std=0.2786)  # data/dataset_builder.py:333-368 with utils/arguments.py defaults
+    want = otransforms.normalize_intensity(otransforms.scale_intensity_range(vol, -1000, 1000, 0.0, 1.0, True), 0.1943, 0.2786)
+    assert np.array_equal(T.test_time_intensity(dv, cfg).cpu().numpy(), want)
+    cfg2 = SimpleNamespace(t_cubed_ct_intensity=True, t_ct_min=-1000, t_ct_max=1000, t_normalize=True, t_norm_mean=0.1943,
+                           t_norm_std=0.2786)
+    want2 = otransforms.normalize_intensity(
+        otransforms.scale_cubed_intensity_range(vol, -1000, 1000, 0.0, 1.0, True, dtype=np.float64), 0.1943, 0.2786)
+    got2 = T.test_time_intensity(dv, cfg2).cpu().numpy()
+    assert np.allclose(got2, want2, rtol=0, atol=1e-6)
+    assert T.test_time_intensity(dv, SimpleNamespace()) is dv

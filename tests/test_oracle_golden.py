@@ -96,3 +96,25 @@ def test_zoom_index_table_host_matches_rule():
         for n_out in list(range(1, 60)) + [155, 240, 333, 1024]:
             assert np.array_equal(zoom_index_table(n_in, n_out), oresample.zoom_index_rule(n_in, n_out)), (n_in, n_out)
     assert zoomed_shape((8, 12, 20), (26, 86, 20)) == (26, 86, 20)
+
+
+from oracle import transforms as otransforms  # noqa: E402
+from tests.golden.cases import INTENSITY_CASES, make_ct_volume  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(INTENSITY_CASES))
+def test_cubed_intensity_scaler_matches_reference_run(name):
+    """oracle.transforms vs outputs of the reference's own ScaleCubedIntensityRange class (data/transforms.py:17-71,
+    AST-extracted and run by make_golden.py under the NumPy recorded in the manifest)."""
+    c = INTENSITY_CASES[name]
+    fx = np.load(os.path.join(GOLD, f"intensity_{name}.npz"))["out"]
+    meta = MANIFEST["intensity"][name]
+    assert sha(fx) == meta["sha256"] and fx.dtype == np.float32
+    vol = make_ct_volume(c)
+    # the fixture was produced under NumPy >= 2: float64 intermediates (see the oracle's precision note)
+    assert int(meta["numpy"].split(".")[0]) >= 2
+    out64 = otransforms.scale_cubed_intensity_range(vol, c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"],
+                                                    dtype=np.float64)
+    assert np.array_equal(out64, fx)
+    out32 = otransforms.scale_cubed_intensity_range(vol, c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"])
+    assert np.max(np.abs(out32 - fx)) <= 2.5e-7 * max(1.0, float(np.abs(fx).max()))  # NumPy < 2 path: <= 1 ulp away
