@@ -37,11 +37,17 @@ def peak():
 
 
 class Flusher:
+    """Evicts the 126 MB L2 between timed launches: 256 MB are written, then a second 256 MB buffer is READ, so the
+    timed kernel starts from an L2 full of clean lines of unrelated data (a write-only flush would leave ~126 MB of
+    dirty lines whose write-back lands inside the timed region - a third of the traffic of a 400 MB kernel)."""
+
     def __init__(self, dev):
         self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.src = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
 
     def __call__(self):
-        self.buf.fill_(1)  # 256 MB > 126 MB L2
+        self.buf.fill_(1)
+        self.src.sum()
 
 
 def timed(fn, reps, flush):
@@ -67,6 +73,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--shape", default="btcv", choices=sorted(SHAPES))
     ap.add_argument("--sw-batch", type=int, default=4)
+    ap.add_argument("--extract-sizes", default="", help="comma-separated window counts for the extract section (profiling)")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     cfg = SHAPES[args.shape]
@@ -107,7 +114,8 @@ def main():
     if want("extract"):
         st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LABELS, sw_batch=B)
         names = {1: "auto (TMA if W starts are 16-byte aligned)", 0: "shifted-vector", 2: "scalar"}
-        for big in (B, 40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))):
+        sizes = [int(x) for x in args.extract_sizes.split(",") if x] or [B, 40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))]
+        for big in sizes:
             for mode in (1, 0, 2):
                 st.use_tma = mode
                 med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)

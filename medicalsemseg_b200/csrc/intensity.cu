@@ -39,28 +39,33 @@ struct Arith<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 };
 
-template <typename T>
-__device__ __forceinline__ float intensity_one(float x0, const IntensityParams& p) {
+// The expensive steps (cube root, the two IEEE divisions) are compile-time switches; rescale, clip and the non-zero
+// mask are cheap and stay runtime flags / neutral bounds.
+template <typename T, bool CBRT, bool SCALE, bool NORM>
+__device__ __forceinline__ float intensity_one(float x0, const IntensityParams& p, T lo, T hi) {
     using A = Arith<T>;
-    if (p.flags & MSS_INT_CBRT) x0 = cbrtf(x0);  // np.cbrt of a float32 array stays float32
+    if (CBRT) x0 = cbrtf(x0);  // np.cbrt of a float32 array stays float32
     T x = static_cast<T>(x0);
-    if (p.flags & MSS_INT_SCALE) x = A::div(A::sub(x, static_cast<T>(p.a_min)), static_cast<T>(p.denom));
+    if (SCALE) x = A::div(A::sub(x, static_cast<T>(p.a_min)), static_cast<T>(p.denom));
     if (p.flags & MSS_INT_RESCALE) x = A::add(A::mul(x, static_cast<T>(p.b_scale)), static_cast<T>(p.b_min));
-    if (p.flags & MSS_INT_CLIP_LO) x = (x < static_cast<T>(p.b_min)) ? static_cast<T>(p.b_min) : x;  // NaN stays NaN
-    if (p.flags & MSS_INT_CLIP_HI) x = (x > static_cast<T>(p.b_max)) ? static_cast<T>(p.b_max) : x;
-    if (p.flags & MSS_INT_NORM) {
+    x = (x < lo) ? lo : x;  // np.clip / torch.clamp: NaN stays NaN; bounds are -inf / +inf when a side is off
+    x = (x > hi) ? hi : x;
+    if (NORM) {
         if (!(p.flags & MSS_INT_NONZERO) || x != static_cast<T>(0))
             x = A::div(A::sub(x, static_cast<T>(p.sub)), static_cast<T>(p.div));
     }
     return static_cast<float>(x);
 }
 
-template <bool VEC, typename T>
+template <bool VEC, typename T, bool CBRT, bool SCALE, bool NORM>
 __global__ void __launch_bounds__(256) intensity_kernel(const float* __restrict__ in, float* __restrict__ out, long long n,
                                                         const IntensityParams p) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long n4 = VEC ? n / 4 : 0;
+    const T inf = static_cast<T>(__int_as_float(0x7f800000));
+    const T lo = (p.flags & MSS_INT_CLIP_LO) ? static_cast<T>(p.b_min) : -inf;
+    const T hi = (p.flags & MSS_INT_CLIP_HI) ? static_cast<T>(p.b_max) : inf;
     constexpr int U = 4;  // independent 16-byte loads in flight per thread
     for (long long i = tid; i < n4; i += stride * U) {
         float4 v[U];
@@ -71,14 +76,29 @@ __global__ void __launch_bounds__(256) intensity_kernel(const float* __restrict_
         for (int u = 0; u < U; ++u)
             if (i + u * stride < n4) {
                 float4 r;
-                r.x = intensity_one<T>(v[u].x, p);
-                r.y = intensity_one<T>(v[u].y, p);
-                r.z = intensity_one<T>(v[u].z, p);
-                r.w = intensity_one<T>(v[u].w, p);
+                r.x = intensity_one<T, CBRT, SCALE, NORM>(v[u].x, p, lo, hi);
+                r.y = intensity_one<T, CBRT, SCALE, NORM>(v[u].y, p, lo, hi);
+                r.z = intensity_one<T, CBRT, SCALE, NORM>(v[u].z, p, lo, hi);
+                r.w = intensity_one<T, CBRT, SCALE, NORM>(v[u].w, p, lo, hi);
                 *reinterpret_cast<float4*>(out + (i + u * stride) * 4) = r;
             }
     }
-    for (long long i = n4 * 4 + tid; i < n; i += stride) out[i] = intensity_one<T>(in[i], p);
+    for (long long i = n4 * 4 + tid; i < n; i += stride) out[i] = intensity_one<T, CBRT, SCALE, NORM>(in[i], p, lo, hi);
+}
+
+template <bool VEC, typename T>
+static void launch_intensity(unsigned nb, cudaStream_t s, const float* in, float* out, long long n, const IntensityParams& p) {
+    const int key = ((p.flags & MSS_INT_CBRT) ? 4 : 0) | ((p.flags & MSS_INT_SCALE) ? 2 : 0) | ((p.flags & MSS_INT_NORM) ? 1 : 0);
+    switch (key) {
+        case 0: intensity_kernel<VEC, T, false, false, false><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 1: intensity_kernel<VEC, T, false, false, true><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 2: intensity_kernel<VEC, T, false, true, false><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 3: intensity_kernel<VEC, T, false, true, true><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 4: intensity_kernel<VEC, T, true, false, false><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 5: intensity_kernel<VEC, T, true, false, true><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        case 6: intensity_kernel<VEC, T, true, true, false><<<nb, 256, 0, s>>>(in, out, n, p); break;
+        default: intensity_kernel<VEC, T, true, true, true><<<nb, 256, 0, s>>>(in, out, n, p); break;
+    }
 }
 
 }  // namespace mss
@@ -111,10 +131,10 @@ extern "C" int mss_intensity_transform(const float* in, float* out, int64_t n, i
     if (blocks > 148LL * 8) blocks = 148LL * 8;
     const unsigned nb = static_cast<unsigned>(blocks);
     cudaStream_t s = as_stream(stream);
-    if (vec && f64) intensity_kernel<true, double><<<nb, 256, 0, s>>>(in, out, n, p);
-    else if (vec) intensity_kernel<true, float><<<nb, 256, 0, s>>>(in, out, n, p);
-    else if (f64) intensity_kernel<false, double><<<nb, 256, 0, s>>>(in, out, n, p);
-    else intensity_kernel<false, float><<<nb, 256, 0, s>>>(in, out, n, p);
+    if (vec && f64) launch_intensity<true, double>(nb, s, in, out, n, p);
+    else if (vec) launch_intensity<true, float>(nb, s, in, out, n, p);
+    else if (f64) launch_intensity<false, double>(nb, s, in, out, n, p);
+    else launch_intensity<false, float>(nb, s, in, out, n, p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }

@@ -69,6 +69,7 @@ constexpr int kRowsPerThread = 4;  // rows a thread gathers per pass (same z-chu
 __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constant__ ResampleParams p) {
     extern __shared__ __align__(16) uint8_t stage[];  // [rp * kRowsPerThread][slot_pitch]
     __shared__ int s_off[256 * kRowsPerThread];       // per slot: byte offset of the row inside its slot, -1 = constant row
+    __shared__ const uint8_t* s_src[256 * kRowsPerThread];
     const int tid = threadIdx.x;
     const int oz = p.out_dims[2], izd = p.in_dims[2], oyd = p.out_dims[1], oxd = p.out_dims[0];
     const int chunk = tid % p.n_chunks, slot = tid / p.n_chunks;
@@ -85,30 +86,41 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
     const int pass_rows = p.rp * kRowsPerThread;
 
     for (int row0 = row_begin; row0 < row_end; row0 += pass_rows) {
-        // ---- stage the source rows of this pass ------------------------------------------------------------
-        for (int v = tid; v < pass_rows * nvec; v += 256) {
-            const int s = v / nvec, j = v - s * nvec;
-            const int row = row0 + s;
-            if (row >= row_end) continue;
-            const int r2 = row / oyd, oy = row - r2 * oyd;
-            const int b = r2 / oxd, ox = r2 - b * oxd;
-            const int sx = __ldg(p.ix + ox), sy = __ldg(p.iy + oy);
-            if (sx < 0 || sy < 0) {
-                if (j == 0) s_off[s] = -1;
-                continue;
+        // ---- where do the source rows of this pass start? (one thread per row) ---------------------------------
+        for (int s2 = tid; s2 < pass_rows; s2 += 256) {
+            const int row = row0 + s2;
+            const uint8_t* src = nullptr;
+            if (row < row_end) {
+                const int r2 = row / oyd, oy = row - r2 * oyd;
+                const int b = r2 / oxd, ox = r2 - b * oxd;
+                const int sx = __ldg(p.ix + ox), sy = __ldg(p.iy + oy);
+                if (sx >= 0 && sy >= 0)
+                    src = p.in + ((static_cast<long long>(b) * p.in_dims[0] + sx) * p.in_dims[1] + sy) * izd;
             }
-            const uint8_t* src = p.in + ((static_cast<long long>(b) * p.in_dims[0] + sx) * p.in_dims[1] + sy) * izd;
-            const int m = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
-            if (j == 0) s_off[s] = m;
+            s_src[s2] = src;
+            s_off[s2] = src != nullptr ? static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u) : -1;
+        }
+        __syncthreads();
+        // ---- stage them: aligned 16-byte asynchronous copies, all in flight together ---------------------------
+        for (int v = tid; v < pass_rows * nvec; v += 256) {
+            const int s2 = v / nvec, j = v - s2 * nvec;
+            const uint8_t* src = s_src[s2];
+            if (src == nullptr) continue;
+            const int m = s_off[s2];
             if (16 * j >= m + izd) continue;  // this vector lies behind the row
             const uint8_t* g = src - m + 16 * j;
-            uint8_t* d = stage + static_cast<size_t>(s) * p.slot_pitch + 16 * j;
+            uint8_t* d = stage + static_cast<size_t>(s2) * p.slot_pitch + 16 * j;
             if (g >= p.in && g + 16 <= in_end) {
-                *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(g));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                                 static_cast<unsigned>(__cvta_generic_to_shared(d))),
+                             "l"(g)
+                             : "memory");
             } else {
                 for (int e = 0; e < 16; ++e) d[e] = (g + e >= p.in && g + e < in_end) ? g[e] : 0;
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- gather -----------------------------------------------------------------------------------------
         if (active) {
