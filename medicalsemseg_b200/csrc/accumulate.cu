@@ -83,6 +83,9 @@ enum : int { kBefore = 0, kNow = 1, kAfter = 2 };
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async8(unsigned smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
 }
@@ -107,13 +110,20 @@ struct Slot;  // one thread's 4 logits of one class in the ring
 template <>
 struct Slot<float> {
     static constexpr int kBytes = 16;
+    static constexpr bool kUnaligned = true;  // a quad at any 4-byte offset can be fetched as four 4-byte copies
     static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async16(s, g); }
+    static __device__ __forceinline__ void fetch_unaligned(unsigned s, const void* g) {
+        const char* b = static_cast<const char*>(g);
+        cp_async4(s, b), cp_async4(s + 4, b + 4), cp_async4(s + 8, b + 8), cp_async4(s + 12, b + 12);
+    }
     static __device__ __forceinline__ float4 read(unsigned s) { return lds_f4(s); }
 };
 template <>
 struct Slot<__half> {
     static constexpr int kBytes = 8;
+    static constexpr bool kUnaligned = false;
     static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
+    static __device__ __forceinline__ void fetch_unaligned(unsigned, const void*) {}
     static __device__ __forceinline__ float4 read(unsigned s) {
         const uint2 r = lds_u2(s);
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
@@ -124,7 +134,9 @@ struct Slot<__half> {
 template <>
 struct Slot<__nv_bfloat16> {
     static constexpr int kBytes = 8;
+    static constexpr bool kUnaligned = false;
     static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
+    static __device__ __forceinline__ void fetch_unaligned(unsigned, const void*) {}
     static __device__ __forceinline__ float4 read(unsigned s) {
         const uint2 r = lds_u2(s);
         return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
@@ -235,13 +247,15 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
     };
 
     // ---- phase 1: who touched / touches / will touch each element; which listed windows feed this quad ------
-    // fast: the window of this launch covers the whole quad 16-byte aligned -> ring pipeline; slow: partial cover
+    // fast: the window of this launch covers the whole quad -> ring pipeline (16-byte copies; four 4-byte copies when
+    // the window sits at an odd W offset such as BraTS' clamped start 59: `unal`); slow: partial cover
     if (tid == 0) s_any_now = 0;
     unsigned before = 0, now = 0, after = 0;
-    unsigned long long fast = 0ull, slow = 0ull;
+    unsigned long long fast = 0ull, slow = 0ull, unal = 0ull;
     auto scan_chunk = [&](int cn, bool flags) {
         fast = 0ull;
         slow = 0ull;
+        unal = 0ull;
         for (int c = 0; c < cn; ++c) {
             const int sw = s_sw[c];
             const unsigned m = cover_mask(s_sh[c], sw);
@@ -252,8 +266,13 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
                 now |= cls == kNow ? m : 0u;
             }
             if (cls == kNow && m != 0u) {
-                if (m == 0xFu && p.vec_ok && (((gw - sw) & 3) == 0)) fast |= 1ull << c;
-                else slow |= 1ull << c;
+                const bool aligned = ((gw - sw) & 3) == 0;
+                if (m == 0xFu && p.vec_ok && (aligned || Slot<LT>::kUnaligned)) {
+                    fast |= 1ull << c;
+                    if (!aligned) unal |= 1ull << c;
+                } else {
+                    slow |= 1ull << c;
+                }
             }
         }
     };
@@ -329,12 +348,21 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
                 constexpr bool kFull = decltype(full_tag)::value;
                 auto issue = [&](int c, int st) {  // start fetching window c of the list into ring stage st
                     if (c < cn && ((fast >> c) & 1ull)) {
-                        cp_async16(ring_w + st * kWStage, p.imp + (s_wofs[c] + hw));
+                        const float* wg = p.imp + (s_wofs[c] + hw);
                         const char* lg = reinterpret_cast<const char*>(s_ptr[c] + hw) + static_cast<size_t>(k0) * R_bytes;
                         const unsigned dst = ring_l + st * kLStage;
+                        if (!((unal >> c) & 1ull)) {
+                            cp_async16(ring_w + st * kWStage, wg);
 #pragma unroll
-                        for (int k = 0; k < KC; ++k)
-                            if (kFull || k < kc) Slot<LT>::fetch(dst + k * kLSlot, lg + static_cast<unsigned>(k) * R_bytes);
+                            for (int k = 0; k < KC; ++k)
+                                if (kFull || k < kc) Slot<LT>::fetch(dst + k * kLSlot, lg + static_cast<unsigned>(k) * R_bytes);
+                        } else {
+                            Slot<float>::fetch_unaligned(ring_w + st * kWStage, wg);
+#pragma unroll
+                            for (int k = 0; k < KC; ++k)
+                                if (kFull || k < kc)
+                                    Slot<LT>::fetch_unaligned(dst + k * kLSlot, lg + static_cast<unsigned>(k) * R_bytes);
+                        }
                     }
                     cp_async_commit();
                 };

@@ -1,0 +1,141 @@
+// Mirror test-time augmentation around the backbone, the nnU-Net-style predictor of the reference
+// (models/segmentors/nnformer_official/neural_network.py:511-568 `_internal_maybe_mirror_and_pred_3D`):
+//   result = 0;  for every enabled mirror m:  result += (1 / n) * flip_m(softmax(net(flip_m(x))))
+// flip_m mirrors the spatial axes named by the bits of m (bit 0 = W, bit 1 = H, bit 2 = D - the reference's
+// torch.flip dims 4, 3, 2).  Two kernels replace the 2 x 8 torch.flip copies and the 8 scaled adds:
+//   mss_flip_copy    - one mirrored copy of the patch batch for the backbone's input;
+//   mss_mirror_merge - reads the n predictions ONCE, un-mirrors on the fly and accumulates them in the reference's
+//                      order with the reference's roundings: fadd_rn(result, fmul_rn(1/n, pred_m)), 1/n a power of two.
+// One thread owns 4 consecutive W voxels of the result; a W mirror reads the mirrored aligned quad and reverses it
+// in registers, so every access stays a 16-byte vector (W % 4 == 0; scalar kernel otherwise).
+#include "common.cuh"
+
+namespace mss {
+
+constexpr int kMaxMirrors = 8;
+
+struct MirrorParams {
+    const float* src[kMaxMirrors];
+    int mask[kMaxMirrors];
+    int n_terms;
+    float scale;
+    float* out;
+    long long n_outer;  // batch * channels
+    int d, h, w;
+};
+
+__device__ __forceinline__ float4 reverse4(float4 v) { return make_float4(v.w, v.z, v.y, v.x); }
+
+template <bool VEC, bool MERGE>
+__global__ void __launch_bounds__(256) mirror_kernel(const __grid_constant__ MirrorParams p) {
+    constexpr int E = VEC ? 4 : 1;
+    const int wq = p.w / E;
+    const long long per = static_cast<long long>(p.d) * p.h * wq;
+    const long long total = per * p.n_outer;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long o = i / per;
+        int r = static_cast<int>(i - o * per);
+        const int q = r % wq;
+        r /= wq;
+        const int y = r % p.h, z = r / p.h;
+        const long long base = o * (static_cast<long long>(p.d) * p.h * p.w);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v[kMaxMirrors];
+#pragma unroll
+        for (int m = 0; m < kMaxMirrors; ++m) {
+            if (m < p.n_terms) {
+                const int mk = p.mask[m];
+                const int zz = (mk & 4) ? p.d - 1 - z : z;
+                const int yy = (mk & 2) ? p.h - 1 - y : y;
+                const int qq = (mk & 1) ? wq - 1 - q : q;
+                const float* s = p.src[m] + base + (static_cast<long long>(zz) * p.h + yy) * p.w + qq * E;
+                if (VEC) {
+                    v[m] = ld_stream_f4(s);
+                    if (mk & 1) v[m] = reverse4(v[m]);
+                } else {
+                    v[m].x = __ldg(s);
+                }
+            }
+        }
+        if (MERGE) {
+#pragma unroll
+            for (int m = 0; m < kMaxMirrors; ++m) {
+                if (m < p.n_terms) {  // result_torch += 1 / num_results * pred   (neural_network.py:537-565)
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(p.scale, v[m].x));
+                    if (VEC) {
+                        acc.y = __fadd_rn(acc.y, __fmul_rn(p.scale, v[m].y));
+                        acc.z = __fadd_rn(acc.z, __fmul_rn(p.scale, v[m].z));
+                        acc.w = __fadd_rn(acc.w, __fmul_rn(p.scale, v[m].w));
+                    }
+                }
+            }
+        } else {
+            acc = v[0];
+        }
+        float* dst = p.out + base + (static_cast<long long>(z) * p.h + y) * p.w + q * E;
+        if (VEC) *reinterpret_cast<float4*>(dst) = acc;
+        else *dst = acc.x;
+    }
+}
+
+static int launch_mirror(const MirrorParams& p, bool merge, cudaStream_t s) {
+    bool vec = p.w % 4 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
+    for (int m = 0; m < p.n_terms; ++m)
+        if (reinterpret_cast<uintptr_t>(p.src[m]) % 16 != 0) vec = false;
+    const long long work = p.n_outer * p.d * p.h * (vec ? p.w / 4 : p.w);
+    long long blocks = (work + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    const unsigned nb = static_cast<unsigned>(blocks);
+    if (vec && merge) mirror_kernel<true, true><<<nb, 256, 0, s>>>(p);
+    else if (vec) mirror_kernel<true, false><<<nb, 256, 0, s>>>(p);
+    else if (merge) mirror_kernel<false, true><<<nb, 256, 0, s>>>(p);
+    else mirror_kernel<false, false><<<nb, 256, 0, s>>>(p);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" int mss_flip_copy(const float* in, float* out, int64_t n_outer, const int32_t dims[3], int32_t mirror_mask,
+                             void* stream) {
+    MSS_REQUIRE(in != nullptr && out != nullptr && dims != nullptr && in != out, MSS_E_ARG,
+                "flip_copy: null argument (or in == out: the copy is not in place)");
+    MSS_REQUIRE(n_outer > 0 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, MSS_E_ARG, "flip_copy: sizes must be positive");
+    MSS_REQUIRE(mirror_mask >= 0 && mirror_mask < 8, MSS_E_ARG, "flip_copy: mirror_mask %d outside [0, 8)", mirror_mask);
+    MirrorParams p;
+    for (int m = 0; m < kMaxMirrors; ++m) p.src[m] = nullptr, p.mask[m] = 0;
+    p.src[0] = in;
+    p.mask[0] = mirror_mask;
+    p.n_terms = 1;
+    p.scale = 1.f;
+    p.out = out;
+    p.n_outer = n_outer;
+    p.d = dims[0], p.h = dims[1], p.w = dims[2];
+    return launch_mirror(p, false, as_stream(stream));
+}
+
+extern "C" int mss_mirror_merge(const float* const* preds, const int32_t* mirror_masks, int32_t n_terms, float scale,
+                                float* out, int64_t n_outer, const int32_t dims[3], void* stream) {
+    MSS_REQUIRE(preds != nullptr && mirror_masks != nullptr && out != nullptr && dims != nullptr, MSS_E_ARG,
+                "mirror_merge: null argument");
+    MSS_REQUIRE(n_terms >= 1 && n_terms <= kMaxMirrors, MSS_E_ARG, "mirror_merge: n_terms %d outside [1, %d]", n_terms,
+                kMaxMirrors);
+    MSS_REQUIRE(n_outer > 0 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, MSS_E_ARG, "mirror_merge: sizes must be positive");
+    MirrorParams p;
+    for (int m = 0; m < kMaxMirrors; ++m) p.src[m] = nullptr, p.mask[m] = 0;
+    for (int m = 0; m < n_terms; ++m) {
+        MSS_REQUIRE(preds[m] != nullptr && preds[m] != out, MSS_E_ARG, "mirror_merge: prediction %d is null or aliases out", m);
+        MSS_REQUIRE(mirror_masks[m] >= 0 && mirror_masks[m] < 8, MSS_E_ARG, "mirror_merge: mask %d outside [0, 8)", mirror_masks[m]);
+        p.src[m] = preds[m];
+        p.mask[m] = mirror_masks[m];
+    }
+    p.n_terms = n_terms;
+    p.scale = scale;
+    p.out = out;
+    p.n_outer = n_outer;
+    p.d = dims[0], p.h = dims[1], p.w = dims[2];
+    return launch_mirror(p, true, as_stream(stream));
+}

@@ -9,8 +9,9 @@
 // the kernels are then pure byte gathers: out[x, y, z] = in[ix[x], iy[y], iz[z]].
 // Rows kernel: a CTA walks a range of output rows (b, x, y) in passes of `rp` rows.  A pass stages its source rows
 // in shared memory with aligned 16-byte copies, then every thread gathers the 16 voxels of its z-chunk from shared
-// memory (its 16 source indices live in registers for the whole kernel: the chunk of a thread never changes) and
-// stores them with one 16-byte store (4-byte / 1-byte stores where the output row is not 16-byte aligned).
+// memory - per output word three aligned 4-byte loads, two funnel shifts and one PRMT whose selector was computed
+// once (the chunk of a thread never changes, so its gather plan lives in registers for the whole kernel) - and
+// stores them with one 16-byte store (funnel-shifted 4-byte stores where the output row is not 16-byte aligned).
 // Gather kernel: the general fallback (rows wider than 4096 voxels or too long for shared memory), byte loads via L1.
 #include <cmath>
 
@@ -78,9 +79,37 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
     const int row_begin = blockIdx.x * p.rows_per_block;
     const int row_end = min(row_begin + p.rows_per_block, n_rows);
     const int nz = min(16, oz - chunk * 16);
-    int zi[16];
+    // Gather plan of this thread's 16 outputs, fixed for the whole kernel: per output word q the first source index,
+    // a PRMT selector of the 4 sources relative to it (valid when they span <= 8 bytes, i.e. zoom factors up to ~2.3)
+    // and a byte mask of the outputs that are real (not past the row, not scipy's constant).
+    int first[4];
+    unsigned sel[4], keep[4];
+    bool narrow = true;
+    {
+        int zi[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) zi[e] = (active && e < nz) ? __ldg(p.iz + chunk * 16 + e) : -1;
+        for (int e = 0; e < 16; ++e) zi[e] = (active && e < nz) ? __ldg(p.iz + chunk * 16 + e) : -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int f = -1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (f < 0 && zi[4 * q + e] >= 0) f = zi[4 * q + e];
+            first[q] = f < 0 ? 0 : f;
+            sel[q] = 0u;
+            keep[q] = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = zi[4 * q + e];
+                if (i >= 0) {
+                    const int rel = i - first[q];
+                    if (rel < 0 || rel > 7) narrow = false;
+                    sel[q] |= static_cast<unsigned>(rel & 7) << (4 * e);
+                    keep[q] |= 0xFFu << (8 * e);
+                }
+            }
+        }
+    }
     const uint8_t* in_end = p.in + p.n_volumes * p.in_dims[0] * p.in_dims[1] * static_cast<long long>(izd);
     const int nvec = p.slot_pitch / 16;
     const int pass_rows = p.rp * kRowsPerThread;
@@ -133,10 +162,27 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
                 const uint8_t* base = stage + static_cast<size_t>(s) * p.slot_pitch + (off < 0 ? 0 : off);
                 unsigned w[4] = {0u, 0u, 0u, 0u};
                 if (off >= 0) {
+                    if (narrow) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const unsigned v = zi[e] >= 0 ? static_cast<unsigned>(base[zi[e]]) : 0u;
-                        w[e >> 2] |= v << (8 * (e & 3));
+                        for (int q = 0; q < 4; ++q) {
+                            // 8 source bytes starting at first[q]: three aligned words, funnel-shifted to the byte
+                            const unsigned pos = static_cast<unsigned>(first[q]) + (base - stage);
+                            const unsigned* wp = reinterpret_cast<const unsigned*>(stage + (pos & ~3u));
+                            const unsigned sh = (pos & 3u) * 8u;
+                            const unsigned a = wp[0], b = wp[1], c = wp[2];
+                            const unsigned lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+                            w[q] = __byte_perm(lo, hi, sel[q]) & keep[q];
+                        }
+                    } else {  // extreme zoom factors: byte by byte
+#pragma unroll 1
+                        for (int e = 0; e < nz; ++e) {
+                            const int i = __ldg(p.iz + chunk * 16 + e);
+                            const unsigned v = i >= 0 ? static_cast<unsigned>(base[i]) : 0u;
+                            if (e < 4) w[0] |= v << (8 * e);
+                            else if (e < 8) w[1] |= v << (8 * (e - 4));
+                            else if (e < 12) w[2] |= v << (8 * (e - 8));
+                            else w[3] |= v << (8 * (e - 12));
+                        }
                     }
                 }
                 store_chunk(p.out + static_cast<long long>(row) * oz + chunk * 16, w, nz);
@@ -220,7 +266,7 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
     const long long n_rows = n_volumes * out_dims[0] * out_dims[1];
     MSS_REQUIRE(n_rows < (1LL << 31), MSS_E_UNSUPPORTED, "resample_nearest: too many output rows for one call");
     p.n_chunks = (out_dims[2] + 15) / 16;
-    p.slot_pitch = (in_dims[2] + 15 + 15) / 16 * 16;
+    p.slot_pitch = (in_dims[2] + 15 + 12 + 15) / 16 * 16;  // row + alignment offset + the 3-word gather window
     constexpr int kMaxStage = 96 * 1024;
     p.rp = p.n_chunks <= 256 ? 256 / p.n_chunks : 0;
     if (p.rp > kMaxStage / (p.slot_pitch * kRowsPerThread)) p.rp = kMaxStage / (p.slot_pitch * kRowsPerThread);
