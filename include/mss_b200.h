@@ -207,6 +207,20 @@ int mss_intensity_transform(const float* in, float* out, int64_t n, int32_t flag
                             double a_max_minus_a_min, double b_min, double b_max, double subtrahend, double divisor,
                             void* stream);
 
+/* ---- mirror test-time augmentation of the nnU-Net-style predictor ------ */
+
+/* out = flip(in) over the spatial axes named by mirror_mask (bit 0 = W, bit 1 = H, bit 2 = D: torch.flip dims
+ * 4, 3, 2 at models/segmentors/nnformer_official/neural_network.py:541-565) for n_outer = batch*channels
+ * volumes of dims (D, H, W).  Not in place. */
+int mss_flip_copy(const float* in, float* out, int64_t n_outer, const int32_t dims[3], int32_t mirror_mask,
+                  void* stream);
+
+/* out = sum over m, in order, of fadd_rn(out, fmul_rn(scale, flip_{mask[m]}(preds[m]))) starting from 0:
+ * `result_torch += 1 / num_results * torch.flip(pred, ...)` of neural_network.py:537-565 for all mirrors in
+ * one pass.  preds[m] are device pointers to [n_outer, D, H, W] fp32; n_terms <= 8; out must not alias. */
+int mss_mirror_merge(const float* const* preds, const int32_t* mirror_masks, int32_t n_terms, float scale,
+                     float* out, int64_t n_outer, const int32_t dims[3], void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,3 +64,29 @@ class ArithmeticPredictor:
             w = w + self.f[k]
             planes.append(w)
         return torch.stack(planes, dim=1).contiguous()
+
+
+class PositionalPredictor:
+    """Plain-tensor predictor that is NOT flip-equivariant (mirror test-time augmentation needs one): every class
+    plane is the channel sum of the patch pushed through one multiply-add and then multiplied by a fixed spatial ramp,
+    ``out[:, k] = (x * a_k + b_k) * ramp_k`` - again only single IEEE float32 multiplies / adds issued as separate
+    torch ops, so CPU and CUDA agree bit for bit."""
+
+    def __init__(self, n_classes: int, patch_size) -> None:
+        self.k = n_classes
+        d, h, w = (int(v) for v in patch_size)
+        zz, yy, xx = torch.meshgrid(torch.arange(d), torch.arange(h), torch.arange(w), indexing="ij")
+        self.ramps = [(1.0 + ((zz * 3 + yy * 5 + xx * 7 + k) % 11).to(torch.float32) * 0.125) for k in range(n_classes)]
+        self.a = [0.5 + 0.25 * k for k in range(n_classes)]
+        self.b = [0.125 * ((k * 3) % 5) - 0.25 for k in range(n_classes)]
+
+    def __call__(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        s = x[:, 0]
+        for c in range(1, x.shape[1]):
+            s = s + x[:, c]
+        planes = []
+        for k in range(self.k):
+            u = s * self.a[k]
+            u = u + self.b[k]
+            planes.append(u * self.ramps[k].to(x.device))
+        return torch.stack(planes, dim=1).contiguous()

@@ -88,3 +88,20 @@ INTENSITY_CASES = {
 def make_ct_volume(case: dict) -> np.ndarray:
     rs = np.random.RandomState(case["seed"])
     return (rs.standard_normal(case["shape"]) * 700.0 - 200.0).astype(np.float32)
+
+
+# nnU-Net-style tiled predictor (models/segmentors/nnformer_official/neural_network.py:300-437, :511-568): seeded volumes
+# [C, X, Y, Z], PositionalPredictor (not flip-equivariant) with an identity non-linearity so CPU and GPU logits agree
+NNUNET_CASES = {
+    "mirror_all": dict(shape=[1, 40, 36, 44], patch=[16, 16, 16], step=0.5, mirror=True, axes=(0, 1, 2), gaussian=True, k=3, seed=51),
+    "mirror_two_axes": dict(shape=[2, 30, 28, 33], patch=[16, 12, 20], step=0.5, mirror=True, axes=(0, 2), gaussian=True, k=4, seed=52),
+    # (use_gaussian=False with more than one tile raises in the reference: its ones-map has the image's shape, :381)
+    "no_mirror": dict(shape=[1, 33, 35, 38], patch=[16, 16, 16], step=0.75, mirror=False, axes=(0, 1, 2), gaussian=True, k=3, seed=53),
+    "padded_single_tile": dict(shape=[1, 10, 14, 16], patch=[16, 16, 16], step=0.5, mirror=True, axes=(0, 1, 2), gaussian=True, k=2, seed=54),
+    "fine_steps": dict(shape=[1, 30, 30, 30], patch=[16, 16, 16], step=0.3, mirror=True, axes=(1,), gaussian=True, k=3, seed=55),
+}
+
+
+def make_nnunet_volume(case: dict) -> np.ndarray:
+    rs = np.random.RandomState(case["seed"])
+    return rs.standard_normal(case["shape"]).astype(np.float32)

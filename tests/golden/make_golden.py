@@ -35,8 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "monai_shim"))
 sys.path.insert(0, REF)
 
 from oracle.predictors import ArithmeticPredictor  # noqa: E402
-from tests.golden.cases import (INTENSITY_CASES, RESAMPLE_CASES, SW_CASES, VOTE_CASES, make_ct_volume,  # noqa: E402
-                                make_label_map, make_volume, make_vote_maps)
+from tests.golden.cases import (INTENSITY_CASES, NNUNET_CASES, RESAMPLE_CASES, SW_CASES, VOTE_CASES,  # noqa: E402
+                                make_ct_volume, make_label_map, make_nnunet_volume, make_volume, make_vote_maps)
 
 
 def sha(a: np.ndarray) -> str:
@@ -87,11 +87,65 @@ def load_reference_cubed_scaler():
     return ns["ScaleCubedIntensityRange"]
 
 
+def load_reference_segmentation_network():
+    """Imports models/segmentors/nnformer_official/neural_network.py itself (unchanged, from /root/reference) with
+    stand-ins for what it imports and this image lacks: batchgenerators' pad_nd_image (restated: oracle.nnunet.pad_to_patch),
+    scipy.ndimage.filters (alias of scipy.ndimage), utils.misc.no_op (a null context manager; utils/misc.py drags in the
+    whole project).  `Tensor.cuda` is made the identity while the reference runs, so its GPU-only code path executes on
+    the CPU with the same float32 arithmetic."""
+    import importlib.util
+    import types
+
+    import scipy.ndimage
+
+    from oracle.nnunet import pad_to_patch
+
+    def pad_nd_image(image, new_shape=None, mode="constant", kwargs=None, return_slicer=False, shape_must_be_divisible_by=None):
+        res, slicer = pad_to_patch(image, new_shape)
+        return res, [slice(0, image.shape[0])] + list(slicer)
+
+    stubs = {
+        "batchgenerators": types.ModuleType("batchgenerators"),
+        "batchgenerators.augmentations": types.ModuleType("batchgenerators.augmentations"),
+        "batchgenerators.augmentations.utils": types.ModuleType("batchgenerators.augmentations.utils"),
+        "utils.misc": types.ModuleType("utils.misc"),
+    }
+    stubs["batchgenerators.augmentations.utils"].pad_nd_image = pad_nd_image
+
+    class no_op:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    stubs["utils.misc"].no_op = no_op
+    if "scipy.ndimage.filters" not in sys.modules:
+        try:
+            import scipy.ndimage.filters  # noqa: F401
+        except Exception:  # noqa: BLE001
+            stubs["scipy.ndimage.filters"] = scipy.ndimage
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        path = os.path.join(REF, "models", "segmentors", "nnformer_official", "neural_network.py")
+        spec = importlib.util.spec_from_file_location("ref_neural_network", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
 def main() -> None:
     torch.set_num_threads(os.cpu_count() or 1)
     from engine.utils import sliding_window_inference as ref_swi  # the reference itself
 
-    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}, "intensity": {}}
+    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}, "intensity": {}, "nnunet": {}}
     for name, c in SW_CASES.items():
         vol = torch.from_numpy(make_volume(c))
         pred = ArithmeticPredictor(c["k"])
@@ -146,6 +200,46 @@ def main() -> None:
         manifest["intensity"][name] = {"sha256": sha(out), "dtype": str(out.dtype), "numpy": np.__version__,
                                        "min": float(out.min()), "max": float(out.max())}
         print("intensity", name, out.shape, out.dtype, sha(out)[:12])
+
+    from oracle.predictors import PositionalPredictor
+    nn_mod = load_reference_segmentation_network()
+
+    class RefNet(nn_mod.SegmentationNetwork):
+        def __init__(self, k, patch):
+            super().__init__()
+            self.num_classes = k
+            self.conv_op = torch.nn.Conv3d
+            self.inference_apply_nonlin = lambda t: t
+            self.pred = PositionalPredictor(k, patch)
+
+        def get_device(self):
+            return 0
+
+        def forward(self, t):
+            return self.pred(t)
+
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, c in NNUNET_CASES.items():
+            vol = make_nnunet_volume(c)
+            net = RefNet(c["k"], c["patch"])
+            with torch.no_grad():
+                seg, probs = net._internal_predict_3D_3Dconv_tiled(
+                    vol, c["step"], c["mirror"], tuple(c["axes"]), tuple(c["patch"]), None, c["gaussian"], "constant",
+                    {"constant_values": 0}, False, False)
+            np.savez_compressed(os.path.join(HERE, f"nnunet_{name}.npz"), seg=seg.astype(np.uint8),
+                                probs=probs.astype(np.float32))
+            manifest["nnunet"][name] = {"sha256_probs": sha(probs.astype(np.float32)), "sha256_seg": sha(seg.astype(np.uint8)),
+                                        "shape": list(probs.shape),
+                                        "steps": nn_mod.SegmentationNetwork._compute_steps_for_sliding_window(
+                                            tuple(c["patch"]), tuple(max(a, b) for a, b in zip(c["shape"][1:], c["patch"])), c["step"])}
+            print("nnunet", name, probs.shape, sha(probs.astype(np.float32))[:12])
+        for ps in [(96, 96, 96), (16, 16, 16), (16, 12, 20)]:
+            g = nn_mod.SegmentationNetwork._get_gaussian(ps, sigma_scale=1.0 / 8)
+            manifest["nnunet"]["gaussian_" + "x".join(map(str, ps))] = {"sha256": sha(g), "min": float(g.min())}
+    finally:
+        torch.Tensor.cuda = real_cuda
 
     # importance maps as the shimmed MONAI-0.8 restatement produces them (unpinned, recorded for drift detection)
     from oracle.monai08 import compute_importance_map

@@ -264,3 +264,53 @@ def test_block_partition_emulated_ranks(name, world, dims):
                                                               [oh[x] - bl[x] for x in range(3)]))
     assert rel_err(logits.cpu(), ref) <= TOL
     assert_labels_match(labels, ref)
+
+
+from oracle.predictors import PositionalPredictor  # noqa: E402
+from tests.golden.cases import NNUNET_CASES, make_nnunet_volume  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(NNUNET_CASES))
+@pytest.mark.parametrize("sw_batch", [1, 3])
+def test_nnunet_tiled_predictor_bit_exact(name, sw_batch):
+    """nnU-Net-style stitching policy + mirror TTA kernels vs the fixtures produced by the reference's own
+    _internal_predict_3D_3Dconv_tiled / _internal_maybe_mirror_and_pred_3D."""
+    from medicalsemseg_b200 import nnunet as N
+    c = NNUNET_CASES[name]
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"nnunet_{name}.npz"))
+    vol = torch.from_numpy(make_nnunet_volume(c)).cuda()
+    st = mss.InferStats()
+    with torch.no_grad():
+        seg, probs = N.predict_3D_tiled(vol, PositionalPredictor(c["k"], c["patch"]), c["patch"], c["step"], c["mirror"],
+                                        tuple(c["axes"]), c["gaussian"], nonlin=lambda t: t, sw_batch_size=sw_batch, stats=st)
+    assert probs.dtype == torch.float32 and seg.dtype == torch.uint8
+    assert torch.equal(probs.cpu(), torch.from_numpy(fx["probs"]))
+    assert np.array_equal(seg.cpu().numpy(), fx["seg"])
+    assert st.gpu_launches > 0
+
+
+def test_mirror_kernels_match_torch_flip():
+    from medicalsemseg_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    for shape in [(2, 3, 8, 12, 16), (1, 2, 7, 9, 10), (1, 1, 16, 16, 15)]:   # W % 4 != 0 takes the scalar kernel
+        x = torch.randn(shape, device="cuda")
+        dims = _lib.I3(*shape[2:])
+        preds, masks = [], []
+        for m in range(8):
+            out = torch.empty_like(x)
+            _lib.check(lib.mss_flip_copy(x.data_ptr(), out.data_ptr(), shape[0] * shape[1], dims, m, stream), "flip")
+            flips = [a for a, bit in ((4, 1), (3, 2), (2, 4)) if m & bit]
+            assert torch.equal(out, torch.flip(x, flips) if flips else x)
+            preds.append(torch.randn(shape, device="cuda"))
+            masks.append(m)
+        want = torch.zeros(shape, device="cuda")
+        for m, p in zip(masks, preds):
+            flips = [a for a, bit in ((4, 1), (3, 2), (2, 4)) if m & bit]
+            want += 1 / 8 * (torch.flip(p, flips) if flips else p)
+        got = torch.empty(shape, device="cuda")
+        ptrs = (C.c_void_p * 8)(*[p.data_ptr() for p in preds])
+        _lib.check(lib.mss_mirror_merge(ptrs, (C.c_int32 * 8)(*masks), 8, 0.125, got.data_ptr(), shape[0] * shape[1], dims,
+                                        stream), "merge")
+        assert torch.equal(got, want)

@@ -118,3 +118,40 @@ def test_cubed_intensity_scaler_matches_reference_run(name):
     assert np.array_equal(out64, fx)
     out32 = otransforms.scale_cubed_intensity_range(vol, c["a_min"], c["a_max"], c["b_min"], c["b_max"], c["clip"])
     assert np.max(np.abs(out32 - fx)) <= 2.5e-7 * max(1.0, float(np.abs(fx).max()))  # NumPy < 2 path: <= 1 ulp away
+
+
+from oracle import nnunet as onnunet  # noqa: E402
+from oracle.predictors import PositionalPredictor  # noqa: E402
+from tests.golden.cases import NNUNET_CASES, make_nnunet_volume  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(NNUNET_CASES))
+def test_nnunet_tiler_matches_reference_run(name):
+    """oracle.nnunet vs outputs of the reference's own SegmentationNetwork._internal_predict_3D_3Dconv_tiled
+    (models/segmentors/nnformer_official/neural_network.py, imported and run by make_golden.py)."""
+    c = NNUNET_CASES[name]
+    fx = np.load(os.path.join(GOLD, f"nnunet_{name}.npz"))
+    meta = MANIFEST["nnunet"][name]
+    assert sha(fx["probs"]) == meta["sha256_probs"] and sha(fx["seg"]) == meta["sha256_seg"]
+    vol = make_nnunet_volume(c)
+    with torch.no_grad():
+        seg, probs = onnunet.predict_3D_tiled(vol, PositionalPredictor(c["k"], c["patch"]), lambda t: t, c["k"], c["patch"],
+                                              c["step"], c["mirror"], tuple(c["axes"]), c["gaussian"])
+    assert np.array_equal(probs, fx["probs"]) and np.array_equal(seg.astype(np.uint8), fx["seg"])
+    image = tuple(max(a, b) for a, b in zip(c["shape"][1:], c["patch"]))
+    assert onnunet.compute_steps(c["patch"], image, c["step"]) == meta["steps"]
+
+
+def test_nnunet_host_policy_matches_reference():
+    from medicalsemseg_b200 import nnunet as N
+    for name, c in NNUNET_CASES.items():
+        image = tuple(max(a, b) for a, b in zip(c["shape"][1:], c["patch"]))
+        assert N.compute_steps_for_sliding_window(c["patch"], image, c["step"]) == MANIFEST["nnunet"][name]["steps"]
+    assert N.compute_steps_for_sliding_window((64, 64, 64), (110, 64, 200), 0.5) == [[0, 23, 46], [0], [0, 27, 54, 82, 109, 136]]
+    for ps in [(96, 96, 96), (16, 16, 16), (16, 12, 20)]:
+        g = N.gaussian_importance_map(ps)  # closed form, no scipy
+        key = "gaussian_" + "x".join(map(str, ps))
+        assert sha(g) == MANIFEST["nnunet"][key]["sha256"]
+        assert np.array_equal(g, onnunet.get_gaussian(ps))
+    assert N._mirror_masks((0, 1, 2), True) == list(range(8)) and N._mirror_masks((0, 2), True) == [0, 1, 4, 5]
+    assert N._mirror_masks((1,), True) == [0, 2] and N._mirror_masks((0, 1, 2), False) == [0]
