@@ -9,7 +9,7 @@ every patch batch, all logits stitched, labels produced.  Workloads (BASELINE.js
 
     btcv       cfg2  1x1x512x512x200, Swin-UNETR-style backbone, K=14, N=400 windows     (default)
     wholebody  cfg3  1x1x512x512x1024, z-slab partitioned across the ranks, N=2100       (--workload wholebody)
-    brats      cfg4  1x4x240x240x155, K=3, one model per rank -> majority vote
+    brats      cfg4  1x4x240x240x155, K=3, 5-model ensemble sharded over the ranks -> majority vote
     cfg1             1x1x128^3, UNet, overlap .25, N=8
 
 With N > 1 ranks the default shards VOLUMES (cfg5: one btcv volume per rank and step, Dice counts all-reduced;
@@ -207,6 +207,10 @@ def main() -> None:
     if args.workload == "wholebody" and world > 1:
         from benchmarks.slab_bench import run_wholebody
         run_wholebody(args, wl, rank, world, dev, dist)
+        return
+    if args.workload == "brats":
+        from benchmarks.ensemble_bench import run_ensemble
+        run_ensemble(args, wl, rank, world, dev, dist)
         return
 
     nb, cin, d, h, w = wl["shape"]

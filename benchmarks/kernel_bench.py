@@ -203,6 +203,20 @@ def main():
                         args.reps, flush)
         report("intensity: cubed scaler (f64 chain)", 8 * ct.numel(), med, mn)
 
+    if want("mirror"):
+        x = torch.randn((B, k, 96, 96, 96), device=dev)
+        outm = torch.empty_like(x)
+        dims3 = _lib.I3(96, 96, 96)
+        med, mn = timed(lambda: _lib.check(lib.mss_flip_copy(x.data_ptr(), outm.data_ptr(), B * k, dims3, 7, stream), "flip"),
+                        args.reps, flush)
+        report(f"mirror flip_copy [{B},{k},96^3] mask=7", 8 * x.numel(), med, mn)
+        preds = [torch.randn_like(x) for _ in range(8)]
+        ptrs8 = (C.c_void_p * 8)(*[t.data_ptr() for t in preds])
+        masks8 = (C.c_int32 * 8)(*range(8))
+        med, mn = timed(lambda: _lib.check(lib.mss_mirror_merge(ptrs8, masks8, 8, 0.125, outm.data_ptr(), B * k, dims3, stream),
+                                           "merge"), args.reps, flush)
+        report(f"mirror merge of 8 [{B},{k},96^3]", 36 * x.numel(), med, mn, "8 reads + 1 write per element")
+
     if want("halo"):
         rows, length = k * 512, 512 * 48
         a = torch.randn(rows, length, device=dev)

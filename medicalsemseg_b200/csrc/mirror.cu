@@ -30,12 +30,10 @@ template <bool VEC, bool MERGE>
 __global__ void __launch_bounds__(256) mirror_kernel(const __grid_constant__ MirrorParams p) {
     constexpr int E = VEC ? 4 : 1;
     const int wq = p.w / E;
-    const long long per = static_cast<long long>(p.d) * p.h * wq;
-    const long long total = per * p.n_outer;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long o = i / per;
-        int r = static_cast<int>(i - o * per);
+    const int per = p.d * p.h * wq;  // < 2^31 (checked by the host); 32-bit index math, volumes on grid.y
+    for (long long o = blockIdx.y; o < p.n_outer; o += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        int r = i;
         const int q = r % wq;
         r /= wq;
         const int y = r % p.h, z = r / p.h;
@@ -83,10 +81,11 @@ static int launch_mirror(const MirrorParams& p, bool merge, cudaStream_t s) {
     bool vec = p.w % 4 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
     for (int m = 0; m < p.n_terms; ++m)
         if (reinterpret_cast<uintptr_t>(p.src[m]) % 16 != 0) vec = false;
-    const long long work = p.n_outer * p.d * p.h * (vec ? p.w / 4 : p.w);
-    long long blocks = (work + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    const unsigned nb = static_cast<unsigned>(blocks);
+    const long long per = static_cast<long long>(p.d) * p.h * (vec ? p.w / 4 : p.w);
+    MSS_REQUIRE(per < (1LL << 31), MSS_E_UNSUPPORTED, "mirror: one volume exceeds 2^31 elements");
+    long long bx = (per + 255) / 256;
+    if (bx > 148LL * 8) bx = 148LL * 8;
+    const dim3 nb(static_cast<unsigned>(bx), static_cast<unsigned>(p.n_outer < 65535 ? p.n_outer : 65535));
     if (vec && merge) mirror_kernel<true, true><<<nb, 256, 0, s>>>(p);
     else if (vec) mirror_kernel<true, false><<<nb, 256, 0, s>>>(p);
     else if (merge) mirror_kernel<false, true><<<nb, 256, 0, s>>>(p);
