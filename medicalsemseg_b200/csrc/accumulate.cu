@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
             // full: all KC classes of this pass exist (no predicates in the unrolled loops)
             auto run = [&](auto full_tag) {
                 constexpr bool kFull = decltype(full_tag)::value;
-                auto issue = [&](int c, int st) {  // start fetching window c of the list (-1: none left) into ring stage st
-                    if (c >= 0 && ((fast >> c) & 1ull)) {
+                auto issue = [&](int c, int st) {  // start fetching window c of the list into ring stage st
+                    if (c < cn && ((fast >> c) & 1ull)) {
                         const float* wg = p.imp + (s_wofs[c] + hw);
                         const char* lg = reinterpret_cast<const char*>(s_ptr[c] + hw) + static_cast<size_t>(k0) * R_bytes;
                         const unsigned dst = ring_l + st * kLStage;
@@ -366,24 +366,15 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
                     }
                     cp_async_commit();
                 };
-                // only the windows that touch this quad are visited (ascending bit order = ascending window order);
-                // the issue cursor runs S - 1 windows ahead of the consume cursor, one commit group per step
-                unsigned long long todo = fast | slow, ahead = todo;
-                auto pop = [](unsigned long long& m) -> int {
-                    const int c = __ffsll(static_cast<long long>(m)) - 1;
-                    m &= m - 1ull;
-                    return c;
-                };
                 int st_issue = 0;
 #pragma unroll
-                for (int i = 0; i < S - 1; ++i) {
-                    issue(pop(ahead), st_issue);
+                for (int c = 0; c < S - 1; ++c) {
+                    issue(c, st_issue);
                     st_issue = st_issue + 1 == S ? 0 : st_issue + 1;
                 }
                 int st_cons = 0;
-                while (todo != 0ull) {
-                    const int c = pop(todo);
-                    issue(pop(ahead), st_issue);
+                for (int c = 0; c < cn; ++c) {
+                    issue(c + S - 1, st_issue);
                     st_issue = st_issue + 1 == S ? 0 : st_issue + 1;
                     cp_async_wait<S - 1>();  // everything up to window c has landed
                     if ((fast >> c) & 1ull) {

@@ -50,13 +50,18 @@ __device__ __forceinline__ void store_chunk(uint8_t* dst, const unsigned (&w)[4]
             return;
         }
         // head bytes up to the next 4-byte boundary, three aligned words built by funnel shifts, tail bytes
-        const unsigned head = 4u - m;
-        for (unsigned e = 0; e < head; ++e) dst[e] = static_cast<uint8_t>(w[0] >> (8 * e));
+        const unsigned head = 4u - m;  // 1..3
+        dst[0] = static_cast<uint8_t>(w[0]);
+        if (head > 1) dst[1] = static_cast<uint8_t>(w[0] >> 8);
+        if (head > 2) dst[2] = static_cast<uint8_t>(w[0] >> 16);
         const unsigned sh = 8u * head;
         *reinterpret_cast<unsigned*>(dst + head) = __funnelshift_r(w[0], w[1], sh);
         *reinterpret_cast<unsigned*>(dst + head + 4) = __funnelshift_r(w[1], w[2], sh);
         *reinterpret_cast<unsigned*>(dst + head + 8) = __funnelshift_r(w[2], w[3], sh);
-        for (unsigned e = 0; e < m; ++e) dst[head + 12 + e] = static_cast<uint8_t>(w[3] >> (sh + 8 * e));
+        const unsigned tail = w[3] >> sh;  // the m = 1..3 last bytes
+        dst[head + 12] = static_cast<uint8_t>(tail);
+        if (m > 1) dst[head + 13] = static_cast<uint8_t>(tail >> 8);
+        if (m > 2) dst[head + 14] = static_cast<uint8_t>(tail >> 16);
         return;
     }
     for (int e = 0; e < nz; ++e) {
@@ -130,22 +135,28 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
             s_off[s2] = src != nullptr ? static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u) : -1;
         }
         __syncthreads();
-        // ---- stage them: aligned 16-byte asynchronous copies, all in flight together ---------------------------
-        for (int v = tid; v < pass_rows * nvec; v += 256) {
-            const int s2 = v / nvec, j = v - s2 * nvec;
+        // ---- stage them: one warp per row, lane j copies the j-th aligned 16-byte vector (asynchronous, all in
+        // flight together); only the first / last rows of the tensor can touch bytes outside it -------------------
+        for (int s2 = tid >> 5; s2 < pass_rows; s2 += 8) {
             const uint8_t* src = s_src[s2];
             if (src == nullptr) continue;
             const int m = s_off[s2];
-            if (16 * j >= m + izd) continue;  // this vector lies behind the row
-            const uint8_t* g = src - m + 16 * j;
-            uint8_t* d = stage + static_cast<size_t>(s2) * p.slot_pitch + 16 * j;
-            if (g >= p.in && g + 16 <= in_end) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                                 static_cast<unsigned>(__cvta_generic_to_shared(d))),
-                             "l"(g)
-                             : "memory");
-            } else {
-                for (int e = 0; e < 16; ++e) d[e] = (g + e >= p.in && g + e < in_end) ? g[e] : 0;
+            const uint8_t* g0 = src - m;
+            uint8_t* d0 = stage + static_cast<size_t>(s2) * p.slot_pitch;
+            const int nv = (m + izd + 15) >> 4;
+            const bool interior = g0 >= p.in && g0 + 16 * nv <= in_end;  // uniform per warp
+            for (int j = tid & 31; j < nv; j += 32) {
+                if (interior) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                                     static_cast<unsigned>(__cvta_generic_to_shared(d0 + 16 * j))),
+                                 "l"(g0 + 16 * j)
+                                 : "memory");
+                } else {
+                    for (int e = 0; e < 16; ++e) {
+                        const uint8_t* g = g0 + 16 * j + e;
+                        d0[16 * j + e] = (g >= p.in && g < in_end) ? *g : 0;
+                    }
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
