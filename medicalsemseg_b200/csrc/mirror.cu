@@ -31,50 +31,63 @@ __global__ void __launch_bounds__(256) mirror_kernel(const __grid_constant__ Mir
     constexpr int E = VEC ? 4 : 1;
     const int wq = p.w / E;
     const int per = p.d * p.h * wq;  // < 2^31 (checked by the host); 32-bit index math, volumes on grid.y
-    for (long long o = blockIdx.y; o < p.n_outer; o += gridDim.y)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
-        int r = i;
-        const int q = r % wq;
-        r /= wq;
-        const int y = r % p.h, z = r / p.h;
-        const long long base = o * (static_cast<long long>(p.d) * p.h * p.w);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v[kMaxMirrors];
-#pragma unroll
-        for (int m = 0; m < kMaxMirrors; ++m) {
-            if (m < p.n_terms) {
-                const int mk = p.mask[m];
-                const int zz = (mk & 4) ? p.d - 1 - z : z;
-                const int yy = (mk & 2) ? p.h - 1 - y : y;
-                const int qq = (mk & 1) ? wq - 1 - q : q;
-                const float* s = p.src[m] + base + (static_cast<long long>(zz) * p.h + yy) * p.w + qq * E;
-                if (VEC) {
-                    v[m] = ld_stream_f4(s);
-                    if (mk & 1) v[m] = reverse4(v[m]);
-                } else {
-                    v[m].x = __ldg(s);
-                }
-            }
-        }
-        if (MERGE) {
+    // volumes per thread and step: the plain flip copy wants 2 loads in flight per thread (98 % of peak), the merge
+    // already has n_terms and wants resident warps instead (U = 2 cost it a third of its bandwidth on B200)
+    constexpr int U = MERGE ? 1 : 2;
+    const long long vol = static_cast<long long>(p.d) * p.h * p.w;
+    for (long long o0 = static_cast<long long>(blockIdx.y) * U; o0 < p.n_outer; o0 += static_cast<long long>(gridDim.y) * U)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+            int r = i;
+            const int q = r % wq;
+            r /= wq;
+            const int y = r % p.h, z = r / p.h;
+            float4 v[U][kMaxMirrors];
 #pragma unroll
             for (int m = 0; m < kMaxMirrors; ++m) {
-                if (m < p.n_terms) {  // result_torch += 1 / num_results * pred   (neural_network.py:537-565)
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(p.scale, v[m].x));
-                    if (VEC) {
-                        acc.y = __fadd_rn(acc.y, __fmul_rn(p.scale, v[m].y));
-                        acc.z = __fadd_rn(acc.z, __fmul_rn(p.scale, v[m].z));
-                        acc.w = __fadd_rn(acc.w, __fmul_rn(p.scale, v[m].w));
+                if (m < p.n_terms) {
+                    const int mk = p.mask[m];
+                    const int zz = (mk & 4) ? p.d - 1 - z : z;
+                    const int yy = (mk & 2) ? p.h - 1 - y : y;
+                    const int qq = (mk & 1) ? wq - 1 - q : q;
+                    const long long off = (static_cast<long long>(zz) * p.h + yy) * p.w + qq * E;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (o0 + u < p.n_outer) {
+                            const float* s = p.src[m] + (o0 + u) * vol + off;
+                            if (VEC) {
+                                v[u][m] = ld_stream_f4(s);
+                                if (mk & 1) v[u][m] = reverse4(v[u][m]);
+                            } else {
+                                v[u][m].x = __ldg(s);
+                            }
+                        }
                     }
                 }
             }
-        } else {
-            acc = v[0];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (o0 + u >= p.n_outer) break;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MERGE) {
+#pragma unroll
+                    for (int m = 0; m < kMaxMirrors; ++m) {
+                        if (m < p.n_terms) {  // result_torch += 1 / num_results * pred   (neural_network.py:537-565)
+                            acc.x = __fadd_rn(acc.x, __fmul_rn(p.scale, v[u][m].x));
+                            if (VEC) {
+                                acc.y = __fadd_rn(acc.y, __fmul_rn(p.scale, v[u][m].y));
+                                acc.z = __fadd_rn(acc.z, __fmul_rn(p.scale, v[u][m].z));
+                                acc.w = __fadd_rn(acc.w, __fmul_rn(p.scale, v[u][m].w));
+                            }
+                        }
+                    }
+                } else {
+                    acc = v[u][0];
+                }
+                float* dst = p.out + (o0 + u) * vol + (static_cast<long long>(z) * p.h + y) * p.w + q * E;
+                if (VEC) *reinterpret_cast<float4*>(dst) = acc;
+                else *dst = acc.x;
+            }
         }
-        float* dst = p.out + base + (static_cast<long long>(z) * p.h + y) * p.w + q * E;
-        if (VEC) *reinterpret_cast<float4*>(dst) = acc;
-        else *dst = acc.x;
-    }
 }
 
 static int launch_mirror(const MirrorParams& p, bool merge, cudaStream_t s) {
@@ -85,7 +98,8 @@ static int launch_mirror(const MirrorParams& p, bool merge, cudaStream_t s) {
     MSS_REQUIRE(per < (1LL << 31), MSS_E_UNSUPPORTED, "mirror: one volume exceeds 2^31 elements");
     long long bx = (per + 255) / 256;
     if (bx > 148LL * 8) bx = 148LL * 8;
-    const dim3 nb(static_cast<unsigned>(bx), static_cast<unsigned>(p.n_outer < 65535 ? p.n_outer : 65535));
+    const long long by = merge ? p.n_outer : (p.n_outer + 1) / 2;
+    const dim3 nb(static_cast<unsigned>(bx), static_cast<unsigned>(by < 65535 ? by : 65535));
     if (vec && merge) mirror_kernel<true, true><<<nb, 256, 0, s>>>(p);
     else if (vec) mirror_kernel<true, false><<<nb, 256, 0, s>>>(p);
     else if (merge) mirror_kernel<false, true><<<nb, 256, 0, s>>>(p);
