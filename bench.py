@@ -184,6 +184,7 @@ def main() -> None:
                     help="windows per backbone call (engine/utils.py sw_batch_size); 8 is 19%% faster than 4 on B200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-gib", type=float, default=None, help="logits held per accumulate launch (default: auto)")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"], help="wholebody, N > 1: how halos travel")
     ap.add_argument("--block-dims", default=None, help="wholebody, N > 1: ranks per axis as DxHxW (default: best balance)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

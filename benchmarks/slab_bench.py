@@ -36,12 +36,14 @@ def run_wholebody(args, wl, rank, world, dev, dist) -> None:
     def step(slab_any, stats=None, time_kernels=False):
         with torch.no_grad():
             st = block.local_pass(slab_any, model, grid, part, rank, "gaussian", sw_batch_size=args.sw_batch, stats=stats,
-                                  time_kernels=time_kernels, volume_is_block=True)
+                                  time_kernels=time_kernels, volume_is_block=True, peer_group=None if p2p else False)
             with st.timer("halo"):
-                halo_bytes[0] = block.exchange_halos(st.acc, part, rank, None)
+                halo_bytes[0] = (block.exchange_halos_p2p(st.acc, part, rank, None) if p2p
+                                 else block.exchange_halos(st.acc, part, rank, None))
             return block.finalize_owned(st, part, rank)
 
     halo_bytes = [0]
+    p2p = getattr(args, "halo", "nccl") == "p2p" and block.can_exchange_p2p(part)
 
     def barrier():
         dist.barrier()
@@ -100,6 +102,7 @@ def run_wholebody(args, wl, rank, world, dev, dist) -> None:
                        "sw_batch": args.sw_batch, "backbone": wl["backbone"] + " (random init, seed 13, fp32 eager torch)",
                        "partition": {"ranks_per_axis_dhw": list(part.dims),
                                      "windows_per_rank": [part.n_windows(i) for i in range(world)],
+                                     "halo": "p2p (symmetric memory, peer reads)" if p2p else "nccl send/recv + add",
                                      "halo_bytes_received_rank0": int(halo_bytes[0])},
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": v * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",

@@ -171,6 +171,13 @@ int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype,
 int mss_halo_add(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t n_rows,
                  int64_t row_len, void* stream);
 
+/* The same reduction over a 5-D box [dims[0..3], row_len] whose innermost dimension is contiguous in both
+ * operands and whose outer dimensions have arbitrary element strides: any face of a block partition in ONE
+ * launch.  `src` may be a peer GPU's accumulator mapped into this process (NVLink peer memory, e.g. a
+ * torch symmetric-memory buffer): the add then IS the transfer - no staging copy, no send/recv. */
+int mss_halo_add_nd(float* dst, const int64_t dst_strides[4], const float* src, const int64_t src_strides[4],
+                    const int64_t dims[4], int64_t row_len, void* stream);
+
 /* ---- after the argmax: back to the original voxel grid ---------------- */
 
 /* Per-axis source-index table of scipy.ndimage.zoom(order=0, prefilter=False, mode='constant') as the

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "mss_majority_vote": (C.c_int, [C.POINTER(vp), c_i32, c_i32, c_i64, vp, vp]),
     "mss_dice_counts": (C.c_int, [vp, vp, c_i32, c_i64, c_i32, vp, vp]),
     "mss_halo_add": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "mss_halo_add_nd": (C.c_int, [vp, c_i64 * 4, vp, c_i64 * 4, c_i64 * 4, c_i64, vp]),
     "mss_zoom_index_table": (C.c_int, [c_i32, c_i32, vp]),
     "mss_resample_nearest": (C.c_int, [vp, I3, vp, I3, c_i64, vp, vp, vp, vp]),
     "mss_flip_copy": (C.c_int, [vp, vp, c_i64, I3, c_i32, vp]),

@@ -98,6 +98,57 @@ def block_partition(grid: WindowGrid, world: int, dims: Optional[Sequence[int]] 
     return BlockPartition(dims, [partition(grid, dims[a], axis=a) for a in range(3)])
 
 
+class PeerAccumulators:
+    """Per-rank fp32 accumulators in torch symmetric memory (CUDA peer mappings over NVLink / NVSwitch): a rank's
+    ``mss_halo_add_nd`` then reads its neighbour's halo planes straight out of the neighbour's accumulator - the add
+    is the transfer, no staging copy, no send/recv, no receive buffer.  One symmetric buffer (sized for the largest
+    block of the partition) is allocated and rendezvoused once per (group, size) and reused for every volume."""
+
+    _cache: dict = {}
+
+    def __init__(self, numel: int, device: torch.device, group: Any = None) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.numel = int(numel)
+        self.buf = symm.empty(self.numel, dtype=torch.float32, device=device)
+        try:
+            self.hdl = symm.rendezvous(self.buf, self.group)
+        except Exception:  # noqa: BLE001 - older torch wants the group enabled explicitly first
+            symm.enable_symm_mem_for_group(self.group.group_name)
+            self.hdl = symm.rendezvous(self.buf, self.group)
+        self.rank = dist.get_rank(self.group)
+
+    @classmethod
+    def get(cls, numel: int, device: torch.device, group: Any = None) -> "PeerAccumulators":
+        key = (id(group), str(device))
+        cur = cls._cache.get(key)
+        if cur is None or cur.numel < numel:
+            cur = cls(numel, device, group)
+            cls._cache[key] = cur
+        return cur
+
+    def local(self, shape: Sequence[int]) -> torch.Tensor:
+        n = 1
+        for v in shape:
+            n *= int(v)
+        return self.buf[:n].view(*shape)
+
+    def remote(self, group_rank: int, shape: Sequence[int]) -> torch.Tensor:
+        """The accumulator of ``group_rank`` (its ``local(shape)``) as a tensor of THIS process, backed by peer memory."""
+        return self.hdl.get_buffer(group_rank, tuple(int(v) for v in shape), torch.float32, 0)
+
+    def barrier(self) -> None:
+        self.hdl.barrier(0)
+
+
+def acc_shape(part: "BlockPartition", rank: int, n_volumes: int, n_classes: int) -> Tuple[int, int, int, int, int]:
+    lo, hi = part.box(rank, "buf")
+    ext = [h - l for l, h in zip(lo, hi)]
+    return (n_volumes, n_classes, ext[0], ext[1], (ext[2] + 3) // 4 * 4)
+
+
 def _box_view(t: torch.Tensor, lo: Sequence[int], hi: Sequence[int]) -> torch.Tensor:
     """View of the buffer-local box [lo, hi) of a ``[..., D, H, W]`` tensor."""
     return t[(Ellipsis, slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2], hi[2]))]
@@ -107,10 +158,11 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
                rank: int, mode: Any = "gaussian", *, sw_batch_size: int = 4, sigma_scale: Any = 0.125, cval: float = 0.0,
                affine: Optional[torch.Tensor] = None, tuple_input: bool = False, tie_tol: float = 1e-5,
                stats: Any = None, time_kernels: bool = False, group_bytes: Optional[int] = None,
-               volume_is_block: bool = False):
+               volume_is_block: bool = False, peer_group: Any = False):
     """Everything rank `rank` does before the exchange: block copy, extract -> backbone -> accumulate of its own
     windows into raw weighted sums over its buffer box.  Returns the Stitcher (``.acc`` is the buffer).
-    ``volume`` is the full volume, or only this rank's buffer box of it when ``volume_is_block``."""
+    ``volume`` is the full volume, or only this rank's buffer box of it when ``volume_is_block``.  ``peer_group``
+    (a process group, or None for the world) places the accumulator in symmetric memory for ``exchange_halos_p2p``."""
     from .importance import importance_map as build_imp
     from .inferer import StitchPlan, Stitcher, _tma_ready
 
@@ -125,8 +177,14 @@ def local_pass(volume: torch.Tensor, model: Callable[..., torch.Tensor], grid: W
         raise ValueError(f"block has spatial shape {tuple(src.shape[2:])}, expected {tuple(extent)}")
     block = _tma_ready(src.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), grid, cval)
     imp = build_imp(grid.roi, mode, sigma_scale, dev)
+    alloc = None
+    if peer_group is not False:
+        def alloc(shape):  # collective: every rank reaches its first predictor batch and asks for the same maximum size
+            k = shape[1]
+            numel = max(int(torch.tensor(acc_shape(part, r, nb, k)).prod()) for r in range(part.world))
+            return PeerAccumulators.get(numel, dev, peer_group).local(shape)
     st = Stitcher(plan, imp, fuse=_lib.FUSE_NONE, sw_batch=sw_batch_size, tie_tol=tie_tol, group_bytes=group_bytes,
-                  stats=stats, time_kernels=time_kernels)
+                  stats=stats, time_kernels=time_kernels, acc_alloc=alloc)
     if stats is not None:
         stats.n_windows = st.total
         stats._near_ties = st.near
@@ -199,6 +257,54 @@ def exchange_halos(acc: torch.Tensor, part: BlockPartition, rank: int, group: An
     return received
 
 
+def can_exchange_p2p(part: BlockPartition) -> bool:
+    """Peer reads need every halo to come from the immediate -1 neighbour only (no forwarding chain: overlap <= 0.5 of
+    the window per cut axis); otherwise the NCCL schedule of ``exchange_halos`` applies."""
+    return not any(part.axes[a].halo_depends_on_previous(i) for a in range(3) for i in range(part.axes[a].world))
+
+
+def exchange_halos_p2p(acc: torch.Tensor, part: BlockPartition, rank: int, group: Any = None,
+                       order: Sequence[int] = (2, 1, 0)) -> int:
+    """The halo reduction of ``exchange_halos`` with peer memory instead of send/recv: after a device-side barrier every
+    rank adds the planes its -1 neighbour wrote beyond its ownership by READING them from the neighbour's accumulator
+    (``mss_halo_add_nd`` with a peer-mapped source).  ``acc`` must come from ``PeerAccumulators`` (``local_pass(...,
+    peer_group=group)``).  Returns the bytes read over NVLink."""
+    import torch.distributed as dist
+
+    if not can_exchange_p2p(part):
+        raise ValueError("this partition needs halo forwarding; use exchange_halos (NCCL)")
+    peers = PeerAccumulators.get(acc.numel(), acc.device, group)
+    nb, k = acc.shape[0], acc.shape[1]
+    c = part.coords(rank)
+    buf_lo, buf_hi = part.box(rank, "buf")
+    own_lo, own_hi = part.box(rank, "own")
+    lo = [0, 0, 0]
+    hi = [h - l for l, h in zip(buf_lo, buf_hi)]
+    moved = 0
+    for a in order:
+        p1, i = part.axes[a], c[a]
+        if p1.world > 1:
+            peers.barrier()  # every accumulator holds what its rank has summed so far
+            if i > 0:
+                rlo, rhi = p1.halo(i - 1)
+                if rhi > rlo:
+                    cc = list(c)
+                    cc[a] -= 1
+                    prev = part.rank_of(cc)
+                    prev_lo, _ = part.box(prev, "buf")
+                    theirs = peers.remote(prev, acc_shape(part, prev, nb, k))
+                    slo, shi = list(lo), list(hi)   # same box in the axes the two ranks share ...
+                    slo[a], shi[a] = rlo - prev_lo[a], rhi - prev_lo[a]   # ... the halo planes in the neighbour's frame
+                    dlo, dhi = list(lo), list(hi)
+                    dlo[a], dhi[a] = rlo - buf_lo[a], rhi - buf_lo[a]
+                    src = _box_view(theirs, slo, shi)
+                    cuda_halo_add(_box_view(acc, dlo, dhi), src)
+                    moved += src.numel() * 4
+        lo[a], hi[a] = own_lo[a] - buf_lo[a], own_hi[a] - buf_lo[a]
+    peers.barrier()  # nobody overwrites an accumulator a neighbour may still be reading
+    return moved
+
+
 def finalize_owned(st: Any, part: BlockPartition, rank: int, tie_tol: float = 1e-5,
                    logits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Normalise (weight count of the GLOBAL grid) + argmax of the box rank `rank` owns -> uint8 ``[Nb, own box]``."""
@@ -234,12 +340,14 @@ def sliding_window_infer_blocks(
     stats: Any = None,
     time_kernels: bool = False,
     group_bytes: Optional[int] = None,
+    halo: str = "nccl",
 ) -> Tuple[torch.Tensor, Tuple[List[int], List[int]], BlockPartition]:
     """Block-partitioned ``sliding_window_infer`` over the ranks of ``group``.
 
     ``volume`` is the FULL ``[Nb, C, D, H, W]`` volume (host or device, identical on every rank); each rank copies
     only its block to its GPU.  Returns ``(labels, (own_lo, own_hi), partition)`` where ``labels`` holds this rank's
-    owned box ``[Nb, ...]`` - or the whole label map on every rank when ``gather=True``.
+    owned box ``[Nb, ...]`` - or the whole label map on every rank when ``gather=True``.  ``halo``: ``"nccl"``
+    (send/recv + add) or ``"p2p"`` (accumulators in symmetric memory, halos read from the neighbour over NVLink).
     """
     import torch.distributed as dist
 
@@ -254,11 +362,12 @@ def sliding_window_infer_blocks(
     part = block_partition(grid, world, dims)
     if tuple_input is None:
         tuple_input = affine is not None
+    p2p = halo == "p2p" and can_exchange_p2p(part)
     st = local_pass(volume, model, grid, part, rank, mode, sw_batch_size=sw_batch_size, sigma_scale=sigma_scale, cval=cval,
                     affine=affine, tuple_input=tuple_input, tie_tol=tie_tol, stats=stats, time_kernels=time_kernels,
-                    group_bytes=group_bytes)
+                    group_bytes=group_bytes, peer_group=group if p2p else False)
     with st.timer("halo"):
-        halo_bytes = exchange_halos(st.acc, part, rank, group)
+        halo_bytes = exchange_halos_p2p(st.acc, part, rank, group) if p2p else exchange_halos(st.acc, part, rank, group)
     if stats is not None:
         stats.halo_bytes = halo_bytes
     own = finalize_owned(st, part, rank, tie_tol)

@@ -153,8 +153,10 @@ class Stitcher:
 
     def __init__(self, plan: StitchPlan, imp: torch.Tensor, *, fuse: int, sw_batch: int, tie_tol: float = 1e-5,
                  group_bytes: Optional[int] = None, stats: Optional[InferStats] = None, time_kernels: bool = False,
-                 use_tma: bool = True, extract_bytes: Optional[int] = None):
+                 use_tma: bool = True, extract_bytes: Optional[int] = None,
+                 acc_alloc: Optional[Callable[[Tuple[int, ...]], torch.Tensor]] = None):
         self.lib = _lib.load()
+        self.acc_alloc = acc_alloc  # where the fp32 accumulator lives (peer-mapped symmetric memory for multi-GPU halos)
         self.extract_bytes = int(extract_bytes) if extract_bytes is not None else (1 << 30)
         self.plan, self.imp, self.fuse, self.sw_batch = plan, imp, fuse, int(sw_batch)
         self.tie_tol = float(tie_tol)
@@ -229,8 +231,9 @@ class Stitcher:
             self.labels = torch.empty((self.plan.n_volumes,) + tuple(ext), dtype=torch.uint8, device=self.device)
         if not (self.fuse == _lib.FUSE_LABELS and single_group):
             # no memset: the kernel reads an accumulator element only after an earlier launch wrote it
-            self.acc = torch.empty((self.plan.n_volumes, self.K, ext[0], ext[1], self.plan.pitch_w), dtype=torch.float32,
-                                   device=self.device)
+            shape = (self.plan.n_volumes, self.K, ext[0], ext[1], self.plan.pitch_w)
+            self.acc = (self.acc_alloc(shape) if self.acc_alloc is not None
+                        else torch.empty(shape, dtype=torch.float32, device=self.device))
             if self.stats is not None:
                 self.stats.accumulator_allocated = True
 

@@ -83,26 +83,24 @@ def _region(t: torch.Tensor, axis: int, lo: int, hi: int) -> torch.Tensor:
 
 
 def cuda_halo_add(dst_view: torch.Tensor, src: torch.Tensor) -> None:
-    """``dst_view += src`` with the library kernel.  ``dst_view`` is a strided view of the accumulator, ``src`` the
-    contiguous block that arrived from the neighbour; both are folded into [n_rows, row_len] with constant pitches."""
-    row_len, fold = 1, dst_view.dim()
-    while fold > 0 and dst_view.stride(fold - 1) == row_len and src.stride(fold - 1) == row_len:
-        row_len *= dst_view.shape[fold - 1]
-        fold -= 1
-    n_rows = dst_view.numel() // row_len
-    if fold == 0:
-        dst_pitch = src_pitch = row_len
-    else:
-        def uniform(t: torch.Tensor) -> bool:
-            return all(t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(fold - 1))
-        if not (uniform(dst_view) and uniform(src)):
-            for i in range(dst_view.shape[0]):  # outer dims advance irregularly: one launch per slice
-                cuda_halo_add(dst_view[i], src[i])
-            return
-        dst_pitch, src_pitch = dst_view.stride(fold - 1), src.stride(fold - 1)
-    rc = _lib.load().mss_halo_add(dst_view.data_ptr(), dst_pitch, src.data_ptr(), src_pitch, n_rows, row_len,
-                                  torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "mss_halo_add")
+    """``dst_view += src`` with the library kernel, one launch.  Both are (strided) views of up to 5 dimensions whose
+    innermost dimension is contiguous - a box of an accumulator; ``src`` may be a peer GPU's memory."""
+    if dst_view.shape != src.shape:
+        raise ValueError(f"halo shapes differ: {tuple(dst_view.shape)} vs {tuple(src.shape)}")
+    if dst_view.dim() > 5 or dst_view.dim() < 1:
+        raise ValueError("halo boxes have 1..5 dimensions")
+    if dst_view.numel() == 0:
+        return
+    if dst_view.stride(-1) != 1 or src.stride(-1) != 1:
+        raise ValueError("the innermost halo dimension must be contiguous")
+    outer = dst_view.dim() - 1
+    dims = [1] * (4 - outer) + list(dst_view.shape[:-1])
+    dst_s = [0] * (4 - outer) + list(dst_view.stride()[:-1])
+    src_s = [0] * (4 - outer) + list(src.stride()[:-1])
+    I4 = _lib.c_i64 * 4
+    rc = _lib.load().mss_halo_add_nd(dst_view.data_ptr(), I4(*dst_s), src.data_ptr(), I4(*src_s), I4(*dims),
+                                     dst_view.shape[-1], torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_halo_add_nd")
 
 
 def exchange_halos(acc: torch.Tensor, part: SlabPartition, rank: int, group: Any = None,

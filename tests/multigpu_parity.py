@@ -49,6 +49,13 @@ def main() -> None:
             labels, part = None, None
         blabels, _bown, bpart = block.sliding_window_infer_blocks(vol, pred, c["roi"], c["overlap"], "gaussian",
                                                                   gather=True, sw_batch_size=3, dims=c.get("dims"))
+        # the same block partition with the halos read from the neighbours' accumulators over NVLink (symmetric memory)
+        p2p_err = None
+        try:
+            plabels, _, _ = block.sliding_window_infer_blocks(vol, pred, c["roi"], c["overlap"], "gaussian", gather=True,
+                                                              sw_batch_size=3, dims=c.get("dims"), halo="p2p")
+        except Exception as e:  # noqa: BLE001 - symmetric memory unavailable on this box: reported, NCCL path stands
+            plabels, p2p_err = None, f"{type(e).__name__}: {e}"[:200]
         torch.cuda.synchronize()
         if rank == 0:
             ref = osw.sliding_window_inference(vol, None, c["roi"], 3, pred, overlap=c["overlap"], mode="gaussian",
@@ -65,7 +72,9 @@ def main() -> None:
             entry.update({
                 "near_tie_voxels": int(near.sum()),
                 "block_dims": list(bpart.dims), "block_windows_per_rank": [bpart.n_windows(r) for r in range(world)],
-                "block_mismatch_vs_oracle": int(((blabels.cpu().numpy() != want) & ~near).sum())})
+                "block_mismatch_vs_oracle": int(((blabels.cpu().numpy() != want) & ~near).sum()),
+                "p2p_used": bool(plabels is not None and block.can_exchange_p2p(bpart)), "p2p_error": p2p_err,
+                "p2p_mismatch_vs_oracle": None if plabels is None else int(((plabels.cpu().numpy() != want) & ~near).sum())})
             results[f"case{ci}"] = entry
 
     # cfg5-style: every rank has its own volume's labels; Dice counts all-reduced must equal the sum of the oracle's
@@ -85,7 +94,8 @@ def main() -> None:
         results["dice_allreduce_exact"] = bool(np.array_equal(counts.cpu().numpy(), want))
         ok = results["dice_allreduce_exact"] and all(
             v.get("mismatch_vs_single_gpu", 0) == 0 and v.get("mismatch_vs_oracle", 0) == 0 and
-            v.get("block_mismatch_vs_oracle", 0) == 0 for kk, v in results.items() if kk.startswith("case"))
+            v.get("block_mismatch_vs_oracle", 0) == 0 and (v.get("p2p_mismatch_vs_oracle") or 0) == 0
+            for kk, v in results.items() if kk.startswith("case"))
         results["world"] = world
         results["ok"] = ok
         print(json.dumps(results))

@@ -321,3 +321,27 @@ def test_test_time_intensity_chain_is_one_launch_equivalent():
     got2 = T.test_time_intensity(dv, cfg2).cpu().numpy()
     assert np.allclose(got2, want2, rtol=0, atol=1e-6)
     assert T.test_time_intensity(dv, SimpleNamespace()) is dv
+
+
+def test_halo_add_nd_strided_boxes():
+    """One launch adds any (strided) face of an accumulator: the boxes block.exchange_halos hands over."""
+    from medicalsemseg_b200.slab import cuda_halo_add
+    acc = torch.randn(2, 3, 10, 12, 16, device="cuda")
+    other = torch.randn(2, 3, 10, 12, 16, device="cuda")
+    for box in [(slice(None), slice(None), slice(2, 9), slice(3, 8), slice(4, 12)),     # interior box, W offset aligned
+                (slice(None), slice(None), slice(0, 10), slice(0, 12), slice(5, 11)),    # unaligned W range
+                (slice(0, 1), slice(1, 3), slice(7, 10), slice(None), slice(None)),      # a D face
+                (slice(None), slice(None), slice(None), slice(8, 12), slice(0, 16))]:    # an H face
+        a = acc.clone()
+        want = a.clone()
+        want[box] += other[box]
+        cuda_halo_add(a[box], other[box])              # strided source (what a peer read looks like)
+        assert torch.equal(a, want)
+        b = acc.clone()
+        cuda_halo_add(b[box], other[box].contiguous())  # contiguous source (what NCCL delivers)
+        assert torch.equal(b, want)
+    v = torch.randn(40, device="cuda")
+    w = torch.randn(40, device="cuda")
+    want = v + w
+    cuda_halo_add(v, w)
+    assert torch.equal(v, want)
