@@ -40,7 +40,6 @@ class InferStats:
     gpu_launches: int = 0                      # kernels of libmss_b200.so launched
     extract_bytes: int = 0                     # algorithmic bytes, SURVEY.md section 8(d)
     accumulate_bytes: int = 0
-    used_tma: bool = False
     accumulator_allocated: bool = False
     _near_ties: Optional[torch.Tensor] = field(default=None, repr=False)
     events: Dict[str, List[Tuple[Any, Any]]] = field(default_factory=dict, repr=False)
