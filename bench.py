@@ -284,9 +284,10 @@ def main() -> None:
         r = ROI**3
         n_acc = max(stats[0].n_accumulate_calls, 1)
         # algorithmic bytes of the accumulate kernel as built: every logit read once (4 N K R), plus the
-        # uint8 label of every voxel written once; a launch that does not hold all windows also reads+writes its
-        # share of the fp32 accumulator (8 V K per extra pass, upper bound).
-        acc_bytes = 4 * n_win * k * r + v + (8 * v * k * (n_acc - 1) if n_acc > 1 else 0)
+        # uint8 label of every voxel written once; when the windows need several launches (cfg3 on one GPU) each launch
+        # boundary leaves a roi-thick slab of unfinished voxels (windows are enumerated D-slowest) whose fp32 sums are
+        # written by one launch and read back by the next: 8 K roi H W bytes per boundary.
+        acc_bytes = 4 * n_win * k * r + v + (n_acc - 1) * 8 * k * ROI * h * w * nb
         acc_ms_step = float(np.mean([m.get("accumulate", 0.0) for m in kms]))
         achieved = acc_bytes / (acc_ms_step * 1e-3) / 1e9 if acc_ms_step > 0 else None
         line = {
@@ -297,7 +298,7 @@ def main() -> None:
                 "workload": args.workload, "baseline_config": wl["cfg"], "shape": list(wl["shape"]), "roi": ROI,
                 "overlap": wl["overlap"], "classes": k, "blend": "gaussian", "windows": n_win, "sw_batch": args.sw_batch,
                 "backbone": wl["backbone"] + " (random init, seed 13, fp32 eager torch)", "volumes_per_step": world,
-                "l2_policy": "inputs larger than L2: 19.8 GB of logits per step stream through the 126 MB L2",
+                "l2_policy": f"inputs larger than L2: {4 * n_win * k * r / 1e9:.1f} GB of logits per step stream through the 126 MB L2",
                 "sharding": "one volume per rank, Dice counts all-reduced (cfg5 style)" if world > 1 else "single GPU",
             },
             "e2e": {"value": v * world * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
