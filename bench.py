@@ -322,7 +322,7 @@ def main() -> None:
             line["roofline_extract"] = {"achieved": 8 * n_win * cin * r / (ext_ms * 1e-3) / 1e9, "unit": "GB/s",
                                         "note": "extract-ahead launches of up to 1 GiB of windows (re-reads of overlapping windows hit L2, "
                                                 "so algorithmic bytes / time can exceed the DRAM copy peak)"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 number
             val, t_full, cores, sample = cpu_reference_sample(wl, repeats=1, warmup=0, sw_batch=args.sw_batch)
             line["cpu_baseline"] = {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))

@@ -95,3 +95,39 @@ def test_block_halo_exchange_reproduces_single_process_sums(world, shape, roi, o
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, shape, roi, overlap, dims, out), nprocs=world, join=True)
         assert dict(out) == {r: True for r in range(world)}
+
+
+def test_partition_invariants_on_random_grids():
+    """Every window belongs to exactly one rank, owned boxes tile the volume, a rank's buffer holds all its windows, and
+    its halo along an axis is exactly what it wrote beyond its ownership - for random shapes, rois, overlaps and worlds."""
+    rs = np.random.RandomState(0)
+    done = 0
+    while done < 60:
+        shape = tuple(int(v) for v in rs.randint(20, 90, 3))
+        roi = tuple(int(v) for v in rs.randint(8, 20, 3))
+        overlap = float(rs.choice([0.0, 0.25, 0.5, 0.6, 0.75]))
+        world = int(rs.choice([1, 2, 3, 4, 6, 8]))
+        g = make_grid(shape, roi, overlap)
+        try:
+            p = block.block_partition(g, world)
+        except ValueError:
+            continue
+        done += 1
+        owner = np.full(g.n_starts, -1)
+        cover = np.zeros(shape, np.int16)
+        for r in range(world):
+            wl, wh = p.win_box(r)
+            assert np.all(owner[wl[0]:wh[0], wl[1]:wh[1], wl[2]:wh[2]] == -1)
+            owner[wl[0]:wh[0], wl[1]:wh[1], wl[2]:wh[2]] = r
+            bl, bh = p.box(r, "buf")
+            ol, oh = p.box(r, "own")
+            cover[ol[0]:oh[0], ol[1]:oh[1], ol[2]:oh[2]] += 1
+            for a in range(3):
+                starts = g.starts[a][wl[a]:wh[a]]
+                assert bl[a] == starts[0] and bh[a] == starts[-1] + g.roi[a]          # buffer = union of its windows
+                assert bl[a] <= ol[a] or p.coords(r)[a] == 0
+                c = p.coords(r)[a]
+                halo = p.axes[a].halo(c)
+                assert halo == ((oh[a], bh[a]) if c + 1 < p.dims[a] else (0, 0))
+        assert np.all(owner >= 0) and np.all(cover == 1)
+        assert max(p.n_windows(r) for r in range(world)) * world >= g.n_windows
