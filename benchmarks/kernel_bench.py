@@ -217,6 +217,16 @@ def main():
                                            "merge"), args.reps, flush)
         report(f"mirror merge of 8 [{B},{k},96^3]", 36 * x.numel(), med, mn, "8 reads + 1 write per element")
 
+    if want("hausdorff"):
+        from medicalsemseg_b200.hausdorff import _edges, squared_edt
+        lab = (torch.arange(v, device=dev).view(d, h, w) // 37 % 5 == 0).to(torch.uint8)  # a sparse, streaky class
+        med, mn = timed(lambda: _edges(lab, 1, (0, 0, 0), (d, h, w)), args.reps, flush)
+        report("hausdorff: mask_edges (1 class, whole volume)", 6 * v, med, mn, "u8 in, u8 + i32 out")
+        _e, h0 = _edges(lab, 1, (0, 0, 0), (d, h, w))
+        med, mn = timed(lambda: squared_edt(h0), args.reps, flush)
+        report("hausdorff: exact squared EDT (3 passes + transpose)", 3 * 16 * v + 8 * v, med, mn,
+               "per pass: in + out + two stack arrays, int32")
+
     if want("halo"):
         rows, length = k * 512, 512 * 48
         a = torch.randn(rows, length, device=dev)

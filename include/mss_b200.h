@@ -228,6 +228,22 @@ int mss_flip_copy(const float* in, float* out, int64_t n_outer, const int32_t di
 int mss_mirror_merge(const float* const* preds, const int32_t* mirror_masks, int32_t n_terms, float scale,
                      float* out, int64_t n_outer, const int32_t dims[3], void* stream);
 
+/* ---- 95th-percentile Hausdorff distance (engine/test.py:31,55-57) -------- */
+
+/* Surface voxels of class `cls` inside the box [box_lo, box_hi) of a uint8 label map [dims] (MONAI
+ * get_mask_edges: binary_erosion XOR mask on the bounding box of pred | gt; outside the box = background; axes
+ * along which the box is one voxel thick are ignored, as the reference squeezes them away).  Writes
+ * edges_out[box] (0/1) and the distance-transform input edt_input_out[box] (0 on edges, 2^29 elsewhere). */
+int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, const int32_t box_lo[3],
+                   const int32_t box_hi[3], uint8_t* edges_out, int32_t* edt_input_out, void* stream);
+
+/* One axis of the exact squared Euclidean distance transform (scipy distance_transform_edt, squared, as
+ * MONAI get_surface_distance uses it): out[x] = min_i (x - i)^2 + in[i] along `axis` of an int32 volume [dims];
+ * entries >= 2^29 mean "no feature".  scratch_s / scratch_t: int32 buffers of the volume's size.  Apply to axes
+ * 0, 1, 2 in turn (any order), ping-ponging in/out.  Not in place. */
+int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
+                 int32_t axis, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,3 +76,43 @@ extern "C" void host_bitplanes_roundtrip(const uint8_t* in32, uint8_t* out32, un
     labels_from_bitplanes32(q, r);
     std::memcpy(out32, r, 32);
 }
+
+// ---- exact EDT line routine (csrc/edt.cuh) run over a whole volume on the host: three passes like the GPU driver ----
+#include "../../medicalsemseg_b200/csrc/edt.cuh"
+#include <vector>
+
+// feature: uint8 mask [d, h, w] (non-zero = feature voxel); out: int32 squared distances (kEdtInf when there is none)
+extern "C" void host_edt_squared(const uint8_t* feature, int d, int h, int w, int* out) {
+    const long long n = static_cast<long long>(d) * h * w;
+    std::vector<int> a(n), b(n), s(n), t(n);
+    for (long long i = 0; i < n; ++i) a[i] = feature[i] ? 0 : mss::kEdtInf;
+    // axis 0 (stride h*w), axis 1 (stride w), axis 2 (stride 1); in-place is not allowed, so ping-pong
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const long long o = static_cast<long long>(y) * w + x;
+            mss::edt_line<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w);
+        }
+    for (int z = 0; z < d; ++z)
+        for (int x = 0; x < w; ++x) {
+            const long long o = static_cast<long long>(z) * h * w + x;
+            mss::edt_line<long long>(b.data() + o, a.data() + o, s.data() + o, t.data() + o, h, w);
+        }
+    for (int z = 0; z < d; ++z)
+        for (int y = 0; y < h; ++y) {
+            const long long o = (static_cast<long long>(z) * h + y) * w;
+            mss::edt_line<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, w, 1);
+        }
+    for (long long i = 0; i < n; ++i) out[i] = b[i];
+}
+
+// surface voxels of class cls inside the box [lo, hi) of a label map [dims], as csrc/hausdorff.cu computes them
+extern "C" void host_mask_edges(const uint8_t* labels, const int* dims, int cls, const int* lo, const int* hi, uint8_t* edges) {
+    const int n[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    const long long sy = dims[2], sz = static_cast<long long>(dims[1]) * dims[2];
+    for (int z = 0; z < n[0]; ++z)
+        for (int y = 0; y < n[1]; ++y)
+            for (int x = 0; x < n[2]; ++x) {
+                const uint8_t* c = labels + (lo[0] + z) * sz + (lo[1] + y) * sy + (lo[2] + x);
+                edges[(static_cast<long long>(z) * n[1] + y) * n[2] + x] = mss::mask_edge_at(c, sz, sy, z, y, x, n, cls) ? 1 : 0;
+            }
+}

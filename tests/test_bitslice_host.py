@@ -73,3 +73,61 @@ def test_dice_chunks_uniform_volume(lib):
     counts = np.zeros((3, 16), np.int64)
     assert lib.host_dice_chunks(pred.ctypes.data, pred.ctypes.data, 14, C.c_longlong(n), counts.ctypes.data) == 0
     assert counts[0, 3] == n and counts[1, 3] == n and counts[2, 3] == n and counts.sum() == 3 * n
+
+
+@pytest.mark.parametrize("shape,density", [((9, 11, 13), 0.05), ((20, 7, 15), 0.01), ((1, 16, 16), 0.1), ((12, 12, 1), 0.3),
+                                           ((17, 19, 23), 0.002), ((8, 8, 8), 1.0), ((6, 5, 4), 0.0), ((30, 3, 31), 0.03)])
+def test_edt_line_routine_matches_scipy(lib, shape, density):
+    """csrc/edt.cuh (the routine the GPU pass kernel runs per line) applied along the three axes on the host: exact
+    squared distances, i.e. scipy.ndimage.distance_transform_edt squared."""
+    from scipy import ndimage
+    rs = np.random.RandomState(int(np.prod(shape)) + int(density * 1000))
+    feat = (rs.random_sample(shape) < density).astype(np.uint8)
+    out = np.zeros(shape, np.int32)
+    lib.host_edt_squared(feat.ctypes.data, shape[0], shape[1], shape[2], out.ctypes.data)
+    if feat.sum() == 0:
+        assert np.all(out == 1 << 29)
+        return
+    want = ndimage.distance_transform_edt(feat == 0)
+    assert np.array_equal(np.sqrt(out.astype(np.float64)), want)
+    assert np.array_equal(out, np.rint(want ** 2).astype(np.int32))
+
+
+def _blobby_labels(rs, shape, k):
+    from scipy import ndimage
+    f = ndimage.gaussian_filter(rs.standard_normal(shape), 2.5)
+    return np.digitize(f, np.quantile(f, np.linspace(0, 1, k + 1)[1:-1])).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape", [(20, 24, 18), (12, 30, 9), (1, 20, 20), (16, 1, 12), (10, 11, 1)])
+def test_mask_edges_rule_matches_monai_restated(lib, shape):
+    """The surface rule of csrc/edt.cuh::mask_edge_at vs oracle.hausdorff.get_mask_edges (binary_erosion XOR mask on
+    the bounding box, squeezed) for every class of blobby random label maps, thin boxes included."""
+    from oracle import hausdorff as oh
+    rs = np.random.RandomState(sum(shape))
+    gt = _blobby_labels(rs, shape, 4)
+    pred = gt.copy()
+    flip = rs.random_sample(shape) < 0.08
+    pred[flip] = rs.randint(0, 4, int(flip.sum()))
+    # a class confined to a single plane / line / voxel of the volume: the reference squeezes those axes away
+    pred[pred == 3] = 2
+    gt[gt == 3] = 2
+    pred[shape[0] // 2, 2:6, 0:min(5, shape[2])] = 3
+    gt[shape[0] // 2, 3:7, 0:min(4, shape[2])] = 3
+    for c in range(4):
+        union = (pred == c) | (gt == c)
+        if not union.any():
+            continue
+        lo, hi = [], []
+        for a in range(3):
+            idx = np.nonzero(union.any(axis=tuple(x for x in range(3) if x != a)))[0]
+            lo.append(int(idx[0])), hi.append(int(idx[-1]) + 1)
+        n = [h - l for l, h in zip(lo, hi)]
+        if all(v == 1 for v in n):
+            continue  # 0-d erosion: not defined by the reference
+        want_p, want_g = oh.get_mask_edges(pred == c, gt == c)
+        for arr, want in ((pred, want_p), (gt, want_g)):
+            got = np.zeros(n, np.uint8)
+            lib.host_mask_edges(np.ascontiguousarray(arr).ctypes.data, (C.c_int * 3)(*shape), c, (C.c_int * 3)(*lo),
+                                (C.c_int * 3)(*hi), got.ctypes.data)
+            assert np.array_equal(np.squeeze(got).astype(bool), want), (c, lo, hi)

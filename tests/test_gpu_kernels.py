@@ -345,3 +345,49 @@ def test_halo_add_nd_strided_boxes():
     want = v + w
     cuda_halo_add(v, w)
     assert torch.equal(v, want)
+
+
+def _blobby(rs, shape, k):
+    from scipy import ndimage
+    f = ndimage.gaussian_filter(rs.standard_normal(shape), 2.5)
+    return np.digitize(f, np.quantile(f, np.linspace(0, 1, k + 1)[1:-1])).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape,k,seed", [((24, 28, 20), 4, 0), ((40, 33, 37), 6, 1), ((16, 50, 12), 3, 2), ((31, 17, 64), 5, 3)])
+def test_hausdorff95_bit_exact_vs_monai_restated(shape, k, seed):
+    """Surface kernel + exact EDT passes + NumPy percentile vs oracle.hausdorff (MONAI 0.8 restated with scipy):
+    integer squared distances make the float64 result bit-identical."""
+    from oracle import hausdorff as oh
+    rs = np.random.RandomState(seed)
+    gt = _blobby(rs, shape, k)
+    pred = gt.copy()
+    flip = rs.random_sample(shape) < 0.06
+    pred[flip] = rs.randint(0, k, int(flip.sum()))
+    pred[pred == k - 1] = 0                       # a class missing from the prediction: inf / nan by NumPy's rules
+    want = oh.hausdorff_distance(pred, gt, k + 1)  # class k is absent from both maps: NaN
+    got = mss.hausdorff_distance(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), k + 1)
+    assert got.dtype == np.float64 and np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(got[k])
+    # the plain maximum (percentile=None) and the directed variant follow the same code path
+    for kw in (dict(percentile=None), dict(directed=True), dict(include_background=False)):
+        assert np.array_equal(mss.hausdorff_distance(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), k + 1, **kw),
+                              oh.hausdorff_distance(pred, gt, k + 1, **kw), equal_nan=True)
+    assert mss.mean_hausdorff(got) == pytest.approx(oh.mean_hausdorff(want), nan_ok=True)
+    # float32 labels as the reference's loaders deliver them
+    gotf = mss.hausdorff_distance(torch.from_numpy(pred).cuda(), torch.from_numpy(gt.astype(np.float32)).cuda()[None, None], k + 1)
+    assert np.array_equal(gotf, want, equal_nan=True)
+
+
+def test_squared_edt_matches_scipy_and_properties():
+    from scipy import ndimage
+    from medicalsemseg_b200.hausdorff import squared_edt
+    rs = np.random.RandomState(4)
+    for shape, dens in [((33, 20, 41), 0.01), ((8, 64, 8), 0.2), ((50, 50, 50), 0.0005)]:
+        feat = rs.random_sample(shape) < dens
+        h0 = torch.from_numpy(np.where(feat, 0, 1 << 29).astype(np.int32)).cuda()
+        got = squared_edt(h0).transpose(1, 2).cpu().numpy()
+        want = ndimage.distance_transform_edt(~feat)
+        assert np.array_equal(np.sqrt(got.astype(np.float64)), want)
+    # identical surfaces: Hausdorff distance 0 for every present class
+    lab = torch.from_numpy(_blobby(rs, (30, 30, 30), 4)).cuda()
+    assert np.array_equal(mss.hausdorff_distance(lab, lab, 4), np.zeros(4))
