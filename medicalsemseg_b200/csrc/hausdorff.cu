@@ -23,19 +23,19 @@ struct EdgeParams {
     int* h;
 };
 
+// grid: x over one (y, x) plane of the box in 32-bit index math, y over its planes
 __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__ EdgeParams p) {
-    const long long total = static_cast<long long>(p.n[0]) * p.n[1] * p.n[2];
     const long long sy = p.dims[2], sz = static_cast<long long>(p.dims[1]) * p.dims[2];
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(i % p.n[2]);
-        const long long r = i / p.n[2];
-        const int y = static_cast<int>(r % p.n[1]), z = static_cast<int>(r / p.n[1]);
-        const uint8_t* c = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + (p.lo[2] + x);
-        const bool edge = mask_edge_at(c, sz, sy, z, y, x, p.n, static_cast<unsigned>(p.cls));
-        p.edges[i] = edge ? 1 : 0;
-        p.h[i] = edge ? 0 : kEdtInf;
-    }
+    const int plane = p.n[1] * p.n[2];
+    for (int z = blockIdx.y; z < p.n[0]; z += gridDim.y)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+            const int y = i / p.n[2], x = i - y * p.n[2];
+            const uint8_t* c = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + (p.lo[2] + x);
+            const bool edge = mask_edge_at(c, sz, sy, z, y, x, p.n, static_cast<unsigned>(p.cls));
+            const long long o = static_cast<long long>(z) * plane + i;
+            p.edges[o] = edge ? 1 : 0;
+            p.h[o] = edge ? 0 : kEdtInf;
+        }
 }
 
 struct EdtParams {
@@ -84,10 +84,11 @@ extern "C" int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int3
     p.cls = cls;
     p.edges = edges_out;
     p.h = edt_input_out;
-    const long long total = static_cast<long long>(p.n[0]) * p.n[1] * p.n[2];
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    mask_edges_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(p);
+    MSS_REQUIRE(static_cast<long long>(p.n[1]) * p.n[2] < (1LL << 31), MSS_E_UNSUPPORTED, "mask_edges: plane too large");
+    long long bx = (static_cast<long long>(p.n[1]) * p.n[2] + 255) / 256;
+    if (bx > 148LL * 4) bx = 148LL * 4;
+    const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(p.n[0] < 65535 ? p.n[0] : 65535));
+    mask_edges_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }
