@@ -227,6 +227,13 @@ def main():
         report("hausdorff: exact squared EDT (3 passes + transpose)", 3 * 16 * v + 8 * v, med, mn,
                "per pass: in + out + two stack arrays, int32")
 
+    if want("loss"):
+        from medicalsemseg_b200 import losses as L
+        lg = torch.randn((1, k, d, h, w), device=dev)
+        lb = torch.randint(0, k, (1, 1, d, h, w), dtype=torch.uint8, device=dev)
+        med, mn = timed(lambda: L.dice_ce_sums(lg, lb), args.reps, flush)
+        report(f"dice_ce_sums K={k}", v * (4 * k + 1), med, mn, "includes the D2H of 3K+1 doubles")
+
     if want("halo"):
         rows, length = k * 512, 512 * 48
         a = torch.randn(rows, length, device=dev)

@@ -244,6 +244,15 @@ int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, co
 int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
                  int32_t axis, void* stream);
 
+/* Sums behind the evaluation loss DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True) of
+ * run_evaluation.py:53 / engine/test.py:48, in one pass over the stitched logits (class c, row r, column x at
+ * logits[c*class_stride + r*row_pitch + x]) and the label map [n_rows, row_len] (label_dtype 0 = uint8,
+ * 1 = float32): ADDS into sums[3K+1] (float64, device) I[c] = sum softmax_c [y==c], P[c] = sum softmax_c^2
+ * (softmax_c when squared_pred == 0), G[c] = #(y==c), and CE = sum -log softmax_y.  K <= 16. */
+int mss_dice_ce_sums(const float* logits, int64_t class_stride, int64_t row_pitch, int64_t n_rows, int32_t row_len,
+                     int32_t n_classes, const void* labels, int32_t label_dtype, int32_t squared_pred, double* sums,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

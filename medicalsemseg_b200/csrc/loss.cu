@@ -1,0 +1,161 @@
+// Dice + cross-entropy of the stitched logits against the label map, the evaluation loss of the reference
+// (run_evaluation.py:53 `DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True)`, applied at engine/test.py:48 on
+// `outputs.cpu(), labels.cpu()`: a 2.9 GB device-to-host copy and a CPU softmax for a cfg2 volume).
+//
+// One pass over the K logit planes (the same streaming pattern as finalize): per voxel softmax in registers, then
+//   I[c] += p_c [y == c],   P[c] += p_c^2 (or p_c),   G[c] += [y == c],   CE += -log p_y
+// reduced per warp with shuffles, per CTA in shared memory and across CTAs with float64 atomics.  The host turns the
+// 3K + 1 sums into the loss (MONAI DiceLoss: 1 - (2 I + 1e-5) / (G + P + 1e-5), mean over classes; CrossEntropyLoss:
+// mean over voxels).  SURVEY.md section 8f rank 4.
+#include "common.cuh"
+
+namespace mss {
+
+constexpr int kLossMaxK = 16;
+constexpr int kLossThreads = 256;
+
+struct LossParams {
+    const float* logits;   // class c, row r, column x at logits[c * class_stride + r * row_pitch + x]
+    const void* labels;    // [rows, row_len] contiguous, uint8 or float32
+    int label_f32;
+    long long class_stride, row_pitch, n_rows;
+    int row_len, K, squared;
+    double* sums;          // [3K + 1]: I[K], P[K], G[K], CE
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kLossThreads) dice_ce_kernel(const __grid_constant__ LossParams p) {
+    __shared__ double sh[3 * kLossMaxK + 1];
+    for (int i = threadIdx.x; i < 3 * kLossMaxK + 1; i += kLossThreads) sh[i] = 0.0;
+    __syncthreads();
+    const int K = p.K;
+    const int nq = (p.row_len + 3) / 4;
+    const long long total = p.n_rows * nq;
+    const bool vec = (p.row_len % 4 == 0) && (p.row_pitch % 4 == 0) && (p.class_stride % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0);
+    const int lane = threadIdx.x & 31;
+    // every lane of a warp runs the same number of iterations (shuffles inside): loop on the warp's first index
+    for (long long i0 = (static_cast<long long>(blockIdx.x) * kLossThreads + (threadIdx.x & ~31)); i0 < total;
+         i0 += static_cast<long long>(gridDim.x) * kLossThreads) {
+        const long long i = i0 + lane;
+        const bool on = i < total;
+        const long long row = on ? i / nq : 0;
+        const int x0 = on ? static_cast<int>(i - row * nq) * 4 : 0;
+        const int nv = on ? min(4, p.row_len - x0) : 0;
+        float v[kLossMaxK][4];
+        const float* src = p.logits + row * p.row_pitch + x0;
+#pragma unroll
+        for (int c = 0; c < kLossMaxK; ++c) {
+            if (c < K) {
+                if (vec && on) {
+                    const float4 f = ld_stream_f4(src + c * p.class_stride);
+                    v[c][0] = f.x, v[c][1] = f.y, v[c][2] = f.z, v[c][3] = f.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[c][e] = e < nv ? __ldg(src + c * p.class_stride + e) : 0.f;
+                }
+            }
+        }
+        int y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            y[e] = -1;
+            if (e < nv) {
+                const long long li = row * p.row_len + x0 + e;
+                y[e] = p.label_f32 ? __float2int_rn(static_cast<const float*>(p.labels)[li])
+                                   : static_cast<int>(static_cast<const uint8_t*>(p.labels)[li]);
+            }
+        }
+        // softmax per voxel (max-subtracted, like torch), log-softmax of the labelled class for the cross-entropy
+        float ce = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < kLossMaxK; ++c)
+                if (c < K) m = fmaxf(m, v[c][e]);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < kLossMaxK; ++c)
+                if (c < K) {
+                    v[c][e] = expf(v[c][e] - m);
+                    s += v[c][e];
+                }
+            const float inv = 1.f / s;
+            float py = 1.f;
+#pragma unroll
+            for (int c = 0; c < kLossMaxK; ++c)
+                if (c < K) {
+                    v[c][e] *= inv;
+                    if (c == y[e]) py = v[c][e];
+                }
+            if (e < nv && y[e] >= 0 && y[e] < K) ce -= logf(py);
+        }
+        ce = warp_sum(ce);
+        if (lane == 0 && ce != 0.f) atomicAdd(&sh[3 * kLossMaxK], static_cast<double>(ce));
+#pragma unroll
+        for (int c = 0; c < kLossMaxK; ++c) {
+            if (c < K) {
+                float inter = 0.f, psq = 0.f, g = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (e < nv) {
+                        const float pc = v[c][e];
+                        psq += p.squared ? pc * pc : pc;
+                        if (y[e] == c) inter += pc, g += 1.f;
+                    }
+                inter = warp_sum(inter);
+                psq = warp_sum(psq);
+                g = warp_sum(g);
+                if (lane == 0) {
+                    if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
+                    atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
+                    if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * K + 1; i += kLossThreads) {
+        const int q = i / K, c = i - q * K;
+        const double val = i == 3 * K ? sh[3 * kLossMaxK] : sh[q * kLossMaxK + c];
+        if (val != 0.0) atomicAdd(p.sums + i, val);
+    }
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" int mss_dice_ce_sums(const float* logits, int64_t class_stride, int64_t row_pitch, int64_t n_rows, int32_t row_len,
+                                int32_t n_classes, const void* labels, int32_t label_dtype, int32_t squared_pred, double* sums,
+                                void* stream) {
+    MSS_REQUIRE(logits && labels && sums, MSS_E_ARG, "dice_ce_sums: null argument");
+    MSS_REQUIRE(n_classes >= 1 && n_classes <= kLossMaxK, MSS_E_UNSUPPORTED, "dice_ce_sums: n_classes %d outside [1, %d]",
+                n_classes, kLossMaxK);
+    MSS_REQUIRE(n_rows > 0 && row_len > 0 && row_pitch >= row_len && class_stride > 0, MSS_E_ARG,
+                "dice_ce_sums: need positive sizes and row_pitch >= row_len");
+    MSS_REQUIRE(label_dtype == 0 || label_dtype == 1, MSS_E_ARG, "dice_ce_sums: label_dtype must be 0 (uint8) or 1 (float32)");
+    LossParams p;
+    p.logits = logits;
+    p.labels = labels;
+    p.label_f32 = label_dtype;
+    p.class_stride = class_stride;
+    p.row_pitch = row_pitch;
+    p.n_rows = n_rows;
+    p.row_len = row_len;
+    p.K = n_classes;
+    p.squared = squared_pred != 0;
+    p.sums = sums;
+    const long long work = n_rows * ((row_len + 3) / 4);
+    long long blocks = (work + kLossThreads - 1) / kLossThreads;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    dice_ce_kernel<<<static_cast<unsigned>(blocks), kLossThreads, 0, as_stream(stream)>>>(p);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}

@@ -42,6 +42,7 @@ def test_argument_errors_are_reported_not_thrown():
     I4 = _lib.c_i64 * 4
     assert lib.mss_halo_add_nd(None, I4(0, 0, 0, 0), None, I4(0, 0, 0, 0), I4(1, 1, 1, 1), 4, None) == -1
     assert lib.mss_zoom_index_table(0, 4, None) == -1
+    assert lib.mss_dice_ce_sums(None, 1, 1, 1, 1, 2, None, 0, 1, None, None) == -1
     assert lib.mss_mask_edges(None, _lib.I3(1, 1, 1), 0, _lib.I3(0, 0, 0), _lib.I3(1, 1, 1), None, None, None) == -1
     assert lib.mss_edt_pass(None, None, None, None, _lib.I3(1, 1, 1), 0, None) == -1
     assert lib.mss_flip_copy(None, None, 1, _lib.I3(1, 1, 1), 0, None) == -1

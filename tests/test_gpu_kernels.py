@@ -391,3 +391,43 @@ def test_squared_edt_matches_scipy_and_properties():
     # identical surfaces: Hausdorff distance 0 for every present class
     lab = torch.from_numpy(_blobby(rs, (30, 30, 30), 4)).cuda()
     assert np.array_equal(mss.hausdorff_distance(lab, lab, 4), np.zeros(4))
+
+
+@pytest.mark.parametrize("shape,k", [((1, 14, 20, 24, 28), 14), ((2, 3, 16, 18, 21), 3), ((1, 5, 9, 10, 13), 5)])
+def test_dice_ce_loss_matches_monai_restated(shape, k):
+    """Fused softmax + Dice/CE sums vs oracle.losses (MONAI DiceCELoss restated with torch on the CPU): a float
+    reduction, so the bar is a relative tolerance (1e-5), not bit equality."""
+    from medicalsemseg_b200 import losses as L
+    from oracle import losses as ol
+    rs = np.random.RandomState(k)
+    logits = torch.from_numpy((rs.standard_normal(shape) * 3).astype(np.float32))
+    labels = torch.from_numpy(rs.randint(0, k, (shape[0], 1) + shape[2:]).astype(np.float32))
+    want, parts = ol.dice_ce_loss(logits, labels)
+    got, gparts = L.dice_ce_loss(logits.cuda(), labels.cuda())
+    assert got == pytest.approx(want, rel=1e-5) and gparts["dice"] == pytest.approx(parts["dice"], rel=1e-5)
+    assert gparts["ce"] == pytest.approx(parts["ce"], rel=1e-5)
+    got8, _ = L.dice_ce_loss(logits.cuda(), labels.to(torch.uint8).cuda())       # uint8 label maps
+    assert got8 == pytest.approx(want, rel=1e-5)
+    for kw in (dict(squared_pred=False), dict(include_background=False), dict(lambda_dice=0.5, lambda_ce=2.0)):
+        assert L.dice_ce_loss(logits.cuda(), labels.cuda(), **kw)[0] == pytest.approx(ol.dice_ce_loss(logits, labels, **kw)[0], rel=1e-5)
+    # on the stitcher's W-pitched logits view (no copy): W = 13 lives in a pitch of 16
+    if shape[-1] % 4:
+        buf = torch.zeros(shape[:-1] + ((shape[-1] + 3) // 4 * 4,), device="cuda")
+        buf[..., :shape[-1]] = logits.cuda()
+        assert L.dice_ce_loss(buf[..., :shape[-1]], labels.cuda())[0] == pytest.approx(want, rel=1e-5)
+
+
+def test_dice_ce_loss_full_size_identities():
+    from medicalsemseg_b200 import losses as L
+    k, d, h, w = 14, 128, 128, 200
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    labels = torch.randint(0, k, (1, 1, d, h, w), device="cuda", generator=gen, dtype=torch.uint8)
+    onehot = torch.nn.functional.one_hot(labels[0, 0].long(), k).permute(3, 0, 1, 2)[None].float()
+    sure = onehot * 40.0   # softmax saturates to the one-hot: Dice -> 0 (up to the smoothing), CE -> 0
+    loss, parts = L.dice_ce_loss(sure, labels)
+    assert abs(parts["dice"]) < 1e-6 and abs(parts["ce"]) < 1e-6 and abs(loss) < 2e-6
+    flat = torch.zeros_like(sure)  # uniform softmax 1/K: CE = log K exactly
+    _, parts = L.dice_ce_loss(flat, labels)
+    assert parts["ce"] == pytest.approx(np.log(k), rel=1e-6)
+    s = L.dice_ce_sums(flat, labels)[0]
+    assert s[2 * k:3 * k].sum() == d * h * w and s[k:2 * k] == pytest.approx(np.full(k, d * h * w / k ** 2), rel=1e-6)
