@@ -4,7 +4,8 @@
 //
 // One pass over the K logit planes (the same streaming pattern as finalize): per voxel softmax in registers, then
 //   I[c] += p_c [y == c],   P[c] += p_c^2 (or p_c),   G[c] += [y == c],   CE += -log p_y
-// reduced per warp with shuffles, per CTA in shared memory and across CTAs with float64 atomics.  The host turns the
+// kept per thread over its quads, then reduced per warp with shuffles, per CTA in shared memory and across CTAs with
+// float64 atomics.  The host turns the
 // 3K + 1 sums into the loss (MONAI DiceLoss: 1 - (2 I + 1e-5) / (G + P + 1e-5), mean over classes; CrossEntropyLoss:
 // mean over voxels).  SURVEY.md section 8f rank 4.
 #include "common.cuh"
@@ -12,7 +13,7 @@
 namespace mss {
 
 constexpr int kLossMaxK = 16;
-constexpr int kLossThreads = 256;
+constexpr int kLossThreads = 128;
 
 struct LossParams {
     const float* logits;   // class c, row r, column x at logits[c * class_stride + r * row_pitch + x]
@@ -29,7 +30,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kLossThreads) dice_ce_kernel(const __grid_constant__ LossParams p) {
+__global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_constant__ LossParams p) {
     __shared__ double sh[3 * kLossMaxK + 1];
     for (int i = threadIdx.x; i < 3 * kLossMaxK + 1; i += kLossThreads) sh[i] = 0.0;
     __syncthreads();
@@ -39,20 +40,43 @@ __global__ void __launch_bounds__(kLossThreads) dice_ce_kernel(const __grid_cons
     const bool vec = (p.row_len % 4 == 0) && (p.row_pitch % 4 == 0) && (p.class_stride % 4 == 0) &&
                      (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0);
     const int lane = threadIdx.x & 31;
-    // every lane of a warp runs the same number of iterations (shuffles inside): loop on the warp's first index
-    for (long long i0 = (static_cast<long long>(blockIdx.x) * kLossThreads + (threadIdx.x & ~31)); i0 < total;
+    // per-thread partial sums over the thread's quads (a few hundred float additions), reduced once at the end
+    float aI[kLossMaxK], aP[kLossMaxK], aG[kLossMaxK], ce = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLossMaxK; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+    auto flush = [&]() {  // warp sums -> float64 in shared memory; every lane of the warp takes part
+        ce = warp_sum(ce);
+        if (lane == 0 && ce != 0.f) atomicAdd(&sh[3 * kLossMaxK], static_cast<double>(ce));
+        ce = 0.f;
+#pragma unroll
+        for (int c = 0; c < kLossMaxK; ++c) {
+            if (c < K) {
+                const float inter = warp_sum(aI[c]), psq = warp_sum(aP[c]), g = warp_sum(aG[c]);
+                if (lane == 0) {
+                    if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
+                    if (psq != 0.f) atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
+                    if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
+                }
+                aI[c] = aP[c] = aG[c] = 0.f;
+            }
+        }
+    };
+    int iters = 0;
+    // the trip count is per warp (lanes past the end idle), so the periodic flush can use full-warp shuffles
+    for (long long i0 = static_cast<long long>(blockIdx.x) * kLossThreads + (threadIdx.x & ~31); i0 < total;
          i0 += static_cast<long long>(gridDim.x) * kLossThreads) {
+        if ((++iters & 63) == 0) flush();  // at most 256 float additions per accumulator between float64 hand-overs
         const long long i = i0 + lane;
-        const bool on = i < total;
-        const long long row = on ? i / nq : 0;
-        const int x0 = on ? static_cast<int>(i - row * nq) * 4 : 0;
-        const int nv = on ? min(4, p.row_len - x0) : 0;
+        if (i >= total) continue;
+        const long long row = i / nq;
+        const int x0 = static_cast<int>(i - row * nq) * 4;
+        const int nv = min(4, p.row_len - x0);
         float v[kLossMaxK][4];
         const float* src = p.logits + row * p.row_pitch + x0;
 #pragma unroll
         for (int c = 0; c < kLossMaxK; ++c) {
             if (c < K) {
-                if (vec && on) {
+                if (vec) {
                     const float4 f = ld_stream_f4(src + c * p.class_stride);
                     v[c][0] = f.x, v[c][1] = f.y, v[c][2] = f.z, v[c][3] = f.w;
                 } else {
@@ -72,9 +96,9 @@ __global__ void __launch_bounds__(kLossThreads) dice_ce_kernel(const __grid_cons
             }
         }
         // softmax per voxel (max-subtracted, like torch), log-softmax of the labelled class for the cross-entropy
-        float ce = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+            if (e >= nv) continue;
             float m = -INFINITY;
 #pragma unroll
             for (int c = 0; c < kLossMaxK; ++c)
@@ -91,35 +115,18 @@ __global__ void __launch_bounds__(kLossThreads) dice_ce_kernel(const __grid_cons
 #pragma unroll
             for (int c = 0; c < kLossMaxK; ++c)
                 if (c < K) {
-                    v[c][e] *= inv;
-                    if (c == y[e]) py = v[c][e];
-                }
-            if (e < nv && y[e] >= 0 && y[e] < K) ce -= logf(py);
-        }
-        ce = warp_sum(ce);
-        if (lane == 0 && ce != 0.f) atomicAdd(&sh[3 * kLossMaxK], static_cast<double>(ce));
-#pragma unroll
-        for (int c = 0; c < kLossMaxK; ++c) {
-            if (c < K) {
-                float inter = 0.f, psq = 0.f, g = 0.f;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (e < nv) {
-                        const float pc = v[c][e];
-                        psq += p.squared ? pc * pc : pc;
-                        if (y[e] == c) inter += pc, g += 1.f;
+                    const float pc = v[c][e] * inv;
+                    aP[c] += p.squared ? pc * pc : pc;
+                    if (c == y[e]) {
+                        py = pc;
+                        aI[c] += pc;
+                        aG[c] += 1.f;
                     }
-                inter = warp_sum(inter);
-                psq = warp_sum(psq);
-                g = warp_sum(g);
-                if (lane == 0) {
-                    if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
-                    atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
-                    if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
                 }
-            }
+            if (y[e] >= 0 && y[e] < K) ce -= logf(py);
         }
     }
+    flush();
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * K + 1; i += kLossThreads) {
         const int q = i / K, c = i - q * K;
@@ -154,7 +161,7 @@ extern "C" int mss_dice_ce_sums(const float* logits, int64_t class_stride, int64
     p.sums = sums;
     const long long work = n_rows * ((row_len + 3) / 4);
     long long blocks = (work + kLossThreads - 1) / kLossThreads;
-    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    if (blocks > 148LL * 3) blocks = 148LL * 3;  // one resident wave: the per-thread partial sums are reduced once per thread
     dice_ce_kernel<<<static_cast<unsigned>(blocks), kLossThreads, 0, as_stream(stream)>>>(p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
