@@ -23,18 +23,26 @@ struct EdgeParams {
     int* h;
 };
 
-// grid: x over one (y, x) plane of the box in 32-bit index math, y over its planes
+// grid: x over the (y, x-chunk) pairs of one plane of the box, y over its planes; a thread walks kEdgeRun voxels of a
+// row with one set of row pointers
+constexpr int kEdgeRun = 8;
+
 __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__ EdgeParams p) {
     const long long sy = p.dims[2], sz = static_cast<long long>(p.dims[1]) * p.dims[2];
-    const int plane = p.n[1] * p.n[2];
+    const int chunks = (p.n[2] + kEdgeRun - 1) / kEdgeRun;
+    const int work = p.n[1] * chunks;
+    const unsigned cls = static_cast<unsigned>(p.cls);
     for (int z = blockIdx.y; z < p.n[0]; z += gridDim.y)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
-            const int y = i / p.n[2], x = i - y * p.n[2];
-            const uint8_t* c = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + (p.lo[2] + x);
-            const bool edge = mask_edge_at(c, sz, sy, z, y, x, p.n, static_cast<unsigned>(p.cls));
-            const long long o = static_cast<long long>(z) * plane + i;
-            p.edges[o] = edge ? 1 : 0;
-            p.h[o] = edge ? 0 : kEdtInf;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < work; i += gridDim.x * blockDim.x) {
+            const int y = i / chunks, x0 = (i - y * chunks) * kEdgeRun;
+            const uint8_t* row = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + p.lo[2];
+            const long long o = (static_cast<long long>(z) * p.n[1] + y) * p.n[2];
+            const int x1 = min(x0 + kEdgeRun, p.n[2]);
+            for (int x = x0; x < x1; ++x) {
+                const bool edge = mask_edge_at(row + x, sz, sy, z, y, x, p.n, cls);
+                p.edges[o + x] = edge ? 1 : 0;
+                p.h[o + x] = edge ? 0 : kEdtInf;
+            }
         }
 }
 
@@ -85,7 +93,7 @@ extern "C" int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int3
     p.edges = edges_out;
     p.h = edt_input_out;
     MSS_REQUIRE(static_cast<long long>(p.n[1]) * p.n[2] < (1LL << 31), MSS_E_UNSUPPORTED, "mask_edges: plane too large");
-    long long bx = (static_cast<long long>(p.n[1]) * p.n[2] + 255) / 256;
+    long long bx = (static_cast<long long>(p.n[1]) * ((p.n[2] + kEdgeRun - 1) / kEdgeRun) + 255) / 256;
     if (bx > 148LL * 4) bx = 148LL * 4;
     const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(p.n[0] < 65535 ? p.n[0] : 65535));
     mask_edges_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);

@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < kLossMaxK; ++c)
                 if (c < K) {
-                    v[c][e] = expf(v[c][e] - m);
+                    v[c][e] = __expf(v[c][e] - m);  // ex2.approx path: ~2 ulp, far inside the 1e-5 bar of a 50 M-term mean
                     s += v[c][e];
                 }
-            const float inv = 1.f / s;
+            const float inv = __fdividef(1.f, s);
             float py = 1.f;
 #pragma unroll
             for (int c = 0; c < kLossMaxK; ++c)
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
                         aG[c] += 1.f;
                     }
                 }
-            if (y[e] >= 0 && y[e] < K) ce -= logf(py);
+            if (y[e] >= 0 && y[e] < K) ce -= __logf(py);
         }
     }
     flush();
