@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libmss_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--threads", "0",
 ]
 
 
