@@ -239,7 +239,7 @@ def main() -> None:
         if dist is None:
             return
         counts = mss.dice_counts(labels[0], label_gt, k)
-        dist.all_reduce(counts)
+        dist.all_reduce(counts)  # cfg5's count all-reduce (per-volume Dice across ranks: metrics.gather_volume_counts)
 
     for _ in range(args.warmup):
         dice_leg(step(dev_vol))

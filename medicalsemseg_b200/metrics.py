@@ -76,3 +76,24 @@ class DiceMeter:
                 means[c] = np.nanmean(col)
         m = float(np.nanmean(means)) if np.any(~np.isnan(means)) else float("nan")
         return means, m
+
+
+def gather_volume_counts(counts: Any, group: Any = None) -> np.ndarray:
+    """Per-volume Dice counts of ALL ranks, ``int64 [N_total, 3, K]`` in rank order (volumes sharded over the GPUs,
+    BASELINE.json configs[4]).  The reference averages Dice per volume (``engine/test.py:59-69``: nan-mean over the
+    batch per class), so the counts travel per volume - 3K int64 each - instead of being summed.  Ranks may hold
+    different numbers of volumes.  Works on whatever device ``counts`` lives on (NCCL for CUDA, gloo for CPU)."""
+    import torch.distributed as dist
+
+    c = counts if isinstance(counts, torch.Tensor) else torch.as_tensor(np.asarray(counts))
+    c = c.reshape(-1, 3, c.shape[-1]).to(torch.int64).contiguous()
+    world = dist.get_world_size(group)
+    n = torch.tensor([c.shape[0]], dtype=torch.int64, device=c.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    n_max = max(int(x.item()) for x in ns)
+    pad = torch.zeros((n_max, 3, c.shape[-1]), dtype=torch.int64, device=c.device)
+    pad[: c.shape[0]] = c
+    bufs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return np.concatenate([b[: int(k.item())].cpu().numpy() for b, k in zip(bufs, ns)], axis=0)

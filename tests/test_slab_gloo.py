@@ -88,3 +88,30 @@ def test_halo_exchange_reproduces_single_process_sums(world, shape, roi, overlap
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, shape, roi, overlap, axis, out), nprocs=world, join=True)
         assert dict(out) == {r: True for r in range(world)}
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from medicalsemseg_b200.metrics import DiceMeter, gather_volume_counts
+        rs = np.random.RandomState(rank)
+        mine = rs.randint(0, 1000, size=(rank + 1, 3, 4)).astype(np.int64)   # rank r holds r + 1 volumes
+        allc = gather_volume_counts(torch.from_numpy(mine))
+        want = np.concatenate([np.random.RandomState(r).randint(0, 1000, size=(r + 1, 3, 4)).astype(np.int64) for r in range(world)])
+        meter = DiceMeter(4)
+        meter.add_counts(allc)
+        means, m = meter.class_means()
+        out[rank] = bool(np.array_equal(allc, want)) and len(meter.per_volume) == sum(r + 1 for r in range(world)) and np.isfinite(m)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_per_volume_dice_counts_gather_across_ranks():
+    """cfg5: volumes sharded over ranks, per-volume counts gathered so the nan-mean rules of engine/test.py:59-69 apply."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gather_worker, args=(3, port, out), nprocs=3, join=True)
+        assert dict(out) == {0: True, 1: True, 2: True}
