@@ -184,6 +184,11 @@ def main():
         report(f"dice_counts u8 labels K={k}", 2 * v, med, mn)
         med, mn = timed(lambda: mss.dice_counts(pred, labf, k, out=out), args.reps, flush)
         report(f"dice_counts f32 labels K={k}", 5 * v, med, mn)
+        if v <= 64 * 1024 * 1024:  # cfg5: a rank evaluates 8 volumes - one batched launch
+            pb = torch.randint(0, k, (8, v), dtype=torch.uint8, device=dev)
+            lb8 = torch.randint(0, k, (8, v), dtype=torch.uint8, device=dev)
+            med, mn = timed(lambda: mss.dice_counts_batched(pb, lb8, k), args.reps, flush)
+            report(f"dice_counts_batched 8 volumes u8 K={k}", 16 * v, med, mn, "per-volume counts, one launch")
 
     if want("resample"):
         from medicalsemseg_b200.resample import resample_3d

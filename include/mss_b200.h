@@ -166,6 +166,12 @@ int mss_majority_vote(const uint8_t* const* maps, int32_t n_maps, int32_t n_clas
 int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
                     int32_t n_classes, long long* counts, void* stream);
 
+/* The same for a batch: pred / label hold n_volumes maps of n_voxels each, back to back; counts is
+ * int64[n_volumes][3][n_classes] (ADDED to).  One launch for all volumes a rank evaluates (BASELINE.json
+ * configs[4]: per-volume Dice, engine/test.py:59-69), so the GPU sees enough work to run at HBM speed. */
+int mss_dice_counts_batched(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
+                            int64_t n_volumes, int32_t n_classes, long long* counts, void* stream);
+
 /* Halo reduction for z-slab partitioning: dst[i] += src[i] over a [n_rows, row_len] fp32 block with
  * independent row pitches (the receiving rank adds its neighbour's partial sums). */
 int mss_halo_add(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t n_rows,

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mss_finalize_labels": (C.c_int, [C.POINTER(Layout), vp, vp, c_i32, I3, I3, vp, c_i32, vp, vp, c_f32, vp, vp]),
     "mss_majority_vote": (C.c_int, [C.POINTER(vp), c_i32, c_i32, c_i64, vp, vp]),
     "mss_dice_counts": (C.c_int, [vp, vp, c_i32, c_i64, c_i32, vp, vp]),
+    "mss_dice_counts_batched": (C.c_int, [vp, vp, c_i32, c_i64, c_i64, c_i32, vp, vp]),
     "mss_halo_add": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
     "mss_halo_add_nd": (C.c_int, [vp, c_i64 * 4, vp, c_i64 * 4, c_i64 * 4, c_i64, vp]),
     "mss_zoom_index_table": (C.c_int, [c_i32, c_i32, vp]),

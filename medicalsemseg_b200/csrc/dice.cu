@@ -68,8 +68,13 @@ struct ChunkRegs<float> {
 
 // KP = ceil(K / 2) class pairs
 template <typename LabelT, int KP>
-__global__ void __launch_bounds__(kDiceThreads) dice_kernel(const uint8_t* __restrict__ pred, const LabelT* __restrict__ label,
-                                                            long long n, int K, long long* __restrict__ counts, int vec_ok) {
+__global__ void __launch_bounds__(kDiceThreads) dice_kernel(const uint8_t* __restrict__ pred_all,
+                                                            const LabelT* __restrict__ label_all, long long n, int K,
+                                                            long long* __restrict__ counts_all, int vec_ok) {
+    // blockIdx.y = volume: a batch of label maps is counted by one launch, each into its own [3][K] slot
+    const uint8_t* __restrict__ pred = pred_all + static_cast<long long>(blockIdx.y) * n;
+    const LabelT* __restrict__ label = label_all + static_cast<long long>(blockIdx.y) * n;
+    long long* __restrict__ counts = counts_all + static_cast<long long>(blockIdx.y) * 3 * K;
     __shared__ unsigned sh[3][16];  // TP, P, Y
     if (threadIdx.x < 48) (&sh[0][0])[threadIdx.x] = 0u;
     __syncthreads();
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(kDiceThreads) dice_kernel(const uint8_t* __res
 }
 
 template <typename LabelT>
-static void launch_dice(unsigned blocks, cudaStream_t s, const uint8_t* pred, const LabelT* label, long long n, int K,
+static void launch_dice(dim3 blocks, cudaStream_t s, const uint8_t* pred, const LabelT* label, long long n, int K,
                         long long* counts, int vec_ok) {
     switch ((K + 1) / 2) {
         case 1: dice_kernel<LabelT, 1><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
@@ -163,24 +168,37 @@ static void launch_dice(unsigned blocks, cudaStream_t s, const uint8_t* pred, co
 
 using namespace mss;
 
-extern "C" int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
-                               int32_t n_classes, long long* counts, void* stream) {
+static int dice_counts_impl(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels, int64_t n_volumes,
+                            int32_t n_classes, long long* counts, void* stream) {
     MSS_REQUIRE(pred != nullptr && label != nullptr && counts != nullptr, MSS_E_ARG, "dice_counts: null argument");
-    MSS_REQUIRE(n_voxels > 0, MSS_E_ARG, "dice_counts: n_voxels must be positive");
+    MSS_REQUIRE(n_voxels > 0 && n_volumes > 0 && n_volumes <= 65535, MSS_E_ARG,
+                "dice_counts: n_voxels must be positive, n_volumes in [1, 65535]");
     MSS_REQUIRE(n_classes >= 1 && n_classes <= 16, MSS_E_UNSUPPORTED, "dice_counts: n_classes %d outside [1, 16]", n_classes);
     MSS_REQUIRE(label_dtype == 0 || label_dtype == 1, MSS_E_ARG, "dice_counts: label_dtype must be 0 (uint8) or 1 (float32)");
     // a block's shared histogram is 32-bit: bound the voxels one block can see below 2^32
     long long blocks = (n_voxels / kDiceChunk + kDiceThreads - 1) / kDiceThreads + 1;
     if (blocks > 148LL * 4) blocks = 148LL * 4;
     MSS_REQUIRE(n_voxels / blocks < (1LL << 31), MSS_E_UNSUPPORTED, "dice_counts: volume too large for one call");
-    const int vec_ok = reinterpret_cast<uintptr_t>(pred) % 16 == 0 && reinterpret_cast<uintptr_t>(label) % 16 == 0;
+    // every volume of a batch must keep the 16-byte alignment of the first one for the vector path
+    const int esz = label_dtype == 0 ? 1 : 4;
+    const int vec_ok = reinterpret_cast<uintptr_t>(pred) % 16 == 0 && reinterpret_cast<uintptr_t>(label) % 16 == 0 &&
+                       (n_volumes == 1 || (n_voxels % 16 == 0 && (n_voxels * esz) % 16 == 0));
     cudaStream_t s = as_stream(stream);
+    const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(n_volumes));
     if (label_dtype == 0)
-        launch_dice<uint8_t>(static_cast<unsigned>(blocks), s, pred, static_cast<const uint8_t*>(label), n_voxels, n_classes,
-                             counts, vec_ok);
+        launch_dice<uint8_t>(grid, s, pred, static_cast<const uint8_t*>(label), n_voxels, n_classes, counts, vec_ok);
     else
-        launch_dice<float>(static_cast<unsigned>(blocks), s, pred, static_cast<const float*>(label), n_voxels, n_classes,
-                           counts, vec_ok);
+        launch_dice<float>(grid, s, pred, static_cast<const float*>(label), n_voxels, n_classes, counts, vec_ok);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
+}
+
+extern "C" int mss_dice_counts(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
+                               int32_t n_classes, long long* counts, void* stream) {
+    return dice_counts_impl(pred, label, label_dtype, n_voxels, 1, n_classes, counts, stream);
+}
+
+extern "C" int mss_dice_counts_batched(const uint8_t* pred, const void* label, int32_t label_dtype, int64_t n_voxels,
+                                       int64_t n_volumes, int32_t n_classes, long long* counts, void* stream) {
+    return dice_counts_impl(pred, label, label_dtype, n_voxels, n_volumes, n_classes, counts, stream);
 }

@@ -41,6 +41,30 @@ def dice_counts(pred: torch.Tensor, label: torch.Tensor, n_classes: int,
     return out
 
 
+def dice_counts_batched(pred: torch.Tensor, label: torch.Tensor, n_classes: int) -> torch.Tensor:
+    """Per-volume counts ``int64[B, 3, K]`` of a batch of label maps ``[B, ...]`` in ONE launch (cfg5: a rank's share of
+    the evaluation set); ``label`` uint8 or integer-valued float32 of the same shape."""
+    if not (pred.is_cuda and label.is_cuda):
+        raise _lib.MssError("dice_counts needs CUDA tensors; there is no CPU fallback")
+    if n_classes > _lib.MAX_DICE_CLASSES:
+        raise _lib.MssError(f"dice_counts supports up to {_lib.MAX_DICE_CLASSES} classes")
+    b = pred.shape[0]
+    pred = pred.to(torch.uint8).reshape(b, -1).contiguous()
+    if label.dtype == torch.uint8:
+        ldt = 0
+    else:
+        label, ldt = label.to(torch.float32), 1
+    label = label.reshape(b, -1).contiguous()
+    if pred.shape != label.shape:
+        raise ValueError(f"pred {tuple(pred.shape)} and label {tuple(label.shape)} differ")
+    out = torch.zeros((b, 3, n_classes), dtype=torch.int64, device=pred.device)
+    with torch.cuda.device(pred.device):
+        rc = _lib.load().mss_dice_counts_batched(pred.data_ptr(), label.data_ptr(), ldt, pred.shape[1], b, int(n_classes),
+                                                 out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_dice_counts_batched")
+    return out
+
+
 def dice_from_counts(counts: Any) -> np.ndarray:
     """``2 TP / (Y + P)`` where ``Y > 0`` else NaN (MONAI compute_meandice), float64, per class (last axis)."""
     c = counts.detach().cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)

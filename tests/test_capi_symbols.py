@@ -38,6 +38,7 @@ def test_argument_errors_are_reported_not_thrown():
     assert lib.mss_gaussian_profile(None, 4, 1.0, 0, None) == -1
     assert lib.mss_majority_vote(None, 1, 2, 10, None, None) == -1
     assert lib.mss_dice_counts(None, None, 0, 10, 3, None, None) == -1
+    assert lib.mss_dice_counts_batched(None, None, 0, 10, 2, 3, None, None) == -1
     assert lib.mss_halo_add(None, 1, None, 1, 1, 1, None) == -1
     I4 = _lib.c_i64 * 4
     assert lib.mss_halo_add_nd(None, I4(0, 0, 0, 0), None, I4(0, 0, 0, 0), I4(1, 1, 1, 1), 4, None) == -1

@@ -431,3 +431,18 @@ def test_dice_ce_loss_full_size_identities():
     assert parts["ce"] == pytest.approx(np.log(k), rel=1e-6)
     s = L.dice_ce_sums(flat, labels)[0]
     assert s[2 * k:3 * k].sum() == d * h * w and s[k:2 * k] == pytest.approx(np.full(k, d * h * w / k ** 2), rel=1e-6)
+
+
+@pytest.mark.parametrize("ldt", ["u8", "f32"])
+@pytest.mark.parametrize("n", [100003, 32 * 4096, 17])
+def test_dice_counts_batched_equals_per_volume(ldt, n):
+    """One launch for a batch of label maps gives the per-volume counts of separate launches (odd n: the volumes of the
+    batch lose their 16-byte alignment and the scalar path must take over)."""
+    rs = np.random.RandomState(n % 1000)
+    b, k = 5, 14
+    pred = rs.randint(0, k + 2, size=(b, n)).astype(np.uint8)
+    lab = rs.randint(0, k + 1, size=(b, n)).astype(np.uint8)
+    lab_t = torch.from_numpy(lab).cuda() if ldt == "u8" else torch.from_numpy(lab.astype(np.float32)).cuda()
+    got = mss.dice_counts_batched(torch.from_numpy(pred).cuda(), lab_t, k).cpu().numpy()
+    for i in range(b):
+        assert np.array_equal(got[i], odice.dice_counts(pred[i], lab[i], k)), i
