@@ -87,6 +87,12 @@ class DiceMeter:
         self.per_volume.append(counts.cpu().numpy())
         return counts
 
+    def update_batch(self, pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        """A batch of volumes ``[B, ...]`` in one launch (``mss_dice_counts_batched``); one Dice vector per volume."""
+        counts = dice_counts_batched(pred, label, self.k)
+        self.per_volume.extend(list(counts.cpu().numpy()))
+        return counts
+
     def add_counts(self, counts: Any) -> None:
         c = counts.detach().cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)
         self.per_volume.extend(list(c.reshape(-1, 3, self.k)))

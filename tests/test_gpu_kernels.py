@@ -446,3 +446,8 @@ def test_dice_counts_batched_equals_per_volume(ldt, n):
     got = mss.dice_counts_batched(torch.from_numpy(pred).cuda(), lab_t, k).cpu().numpy()
     for i in range(b):
         assert np.array_equal(got[i], odice.dice_counts(pred[i], lab[i], k)), i
+    meter, single = mss.DiceMeter(k), mss.DiceMeter(k)
+    meter.update_batch(torch.from_numpy(pred).cuda(), lab_t)
+    for i in range(b):
+        single.update(torch.from_numpy(pred[i]).cuda(), lab_t[i])
+    assert np.allclose(meter.class_means()[0], single.class_means()[0], equal_nan=True)
