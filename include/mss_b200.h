@@ -239,7 +239,8 @@ int mss_mirror_merge(const float* const* preds, const int32_t* mirror_masks, int
 /* Surface voxels of class `cls` inside the box [box_lo, box_hi) of a uint8 label map [dims] (MONAI
  * get_mask_edges: binary_erosion XOR mask on the bounding box of pred | gt; outside the box = background; axes
  * along which the box is one voxel thick are ignored, as the reference squeezes them away).  Writes
- * edges_out[box] (0/1) and the distance-transform input edt_input_out[box] (0 on edges, 2^29 elsewhere). */
+ * edges_out[box] (0/1) and, when edt_input_out is not NULL, the int32 distance-transform input (0 on edges, 2^29
+ * elsewhere; not needed when the first pass is mss_edt_pass_mask). */
 int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, const int32_t box_lo[3],
                    const int32_t box_hi[3], uint8_t* edges_out, int32_t* edt_input_out, void* stream);
 
@@ -249,6 +250,11 @@ int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, co
  * 0, 1, 2 in turn (any order), ping-ponging in/out.  Not in place. */
 int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
                  int32_t axis, void* stream);
+
+/* The first pass straight from a uint8 feature mask [dims] (non-zero = feature voxel): saves writing and reading the
+ * int32 input volume. */
+int mss_edt_pass_mask(const uint8_t* mask, int32_t* out, int32_t* scratch_s, int32_t* scratch_t,
+                      const int32_t dims[3], int32_t axis, void* stream);
 
 /* Sums behind the evaluation loss DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True) of
  * run_evaluation.py:53 / engine/test.py:48, in one pass over the stitched logits (class c, row r, column x at

@@ -19,15 +19,16 @@ namespace mss {
 
 constexpr int kEdtInf = 1 << 29;  // "no feature": larger than any squared distance in a volume of side < 2^14
 
-// s / t: the parabola stack of the line (positions and take-over points), n ints each, same stride as everything else.
-template <typename Idx>
-MSS_EDT_HD void edt_line(const int* h, int* out, int* s, int* t, int n, Idx stride) {
+// s / t: the parabola stack of the line (positions and take-over points), n ints each, strided like the line itself.
+// h(u) returns the line's input at position u (a functor, so the first pass can read the uint8 surface mask directly).
+template <typename Idx, typename HFn>
+MSS_EDT_HD void edt_line_fn(HFn h, int* out, int* s, int* t, int n, Idx stride) {
     int q = -1;  // top of the stack
     for (int u = 0; u < n; ++u) {
-        const long long hu = h[u * stride];
+        const long long hu = h(u);
         if (hu >= kEdtInf) continue;
         while (q >= 0) {
-            const long long i = s[q * stride], hi = h[i * stride], x = t[q * stride];
+            const long long i = s[q * stride], hi = h(static_cast<int>(i)), x = t[q * stride];
             // parabola u is at or below parabola i at the point where i took over: i never wins
             if ((x - i) * (x - i) + hi > (x - u) * (x - u) + hu) --q;
             else break;
@@ -37,7 +38,7 @@ MSS_EDT_HD void edt_line(const int* h, int* out, int* s, int* t, int n, Idx stri
             s[0] = u;
             t[0] = 0;
         } else {
-            const long long i = s[q * stride], hi = h[i * stride];
+            const long long i = s[q * stride], hi = h(static_cast<int>(i));
             // first integer x where parabola u is strictly below parabola i (u > i):  x > (u^2 - i^2 + hu - hi) / (2 (u - i))
             const long long num = static_cast<long long>(u) * u - i * i + hu - hi, den = 2 * (u - i);
             long long w = num >= 0 ? num / den : -((-num + den - 1) / den);  // floor division
@@ -56,9 +57,20 @@ MSS_EDT_HD void edt_line(const int* h, int* out, int* s, int* t, int n, Idx stri
     for (int x = n - 1; x >= 0; --x) {
         while (q > 0 && t[q * stride] > x) --q;
         const long long i = s[q * stride];
-        const long long v = (x - i) * (x - i) + h[i * stride];
+        const long long v = (x - i) * (x - i) + h(static_cast<int>(i));
         out[x * stride] = v >= kEdtInf ? kEdtInf : static_cast<int>(v);
     }
+}
+
+template <typename Idx>
+MSS_EDT_HD void edt_line(const int* h, int* out, int* s, int* t, int n, Idx stride) {
+    edt_line_fn<Idx>([h, stride](int u) -> long long { return h[u * stride]; }, out, s, t, n, stride);
+}
+
+// first pass straight from a uint8 feature mask: h = 0 on features, "none" elsewhere
+template <typename Idx>
+MSS_EDT_HD void edt_line_mask(const unsigned char* m, int* out, int* s, int* t, int n, Idx stride) {
+    edt_line_fn<Idx>([m, stride](int u) -> long long { return m[u * stride] ? 0 : kEdtInf; }, out, s, t, n, stride);
 }
 
 // Is the voxel at `c` (class `cls`, position (z, y, x) inside a box of n[0] x n[1] x n[2] voxels, strides sz / sy / 1)

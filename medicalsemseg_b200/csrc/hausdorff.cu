@@ -41,13 +41,14 @@ __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__
             for (int x = x0; x < x1; ++x) {
                 const bool edge = mask_edge_at(row + x, sz, sy, z, y, x, p.n, cls);
                 p.edges[o + x] = edge ? 1 : 0;
-                p.h[o + x] = edge ? 0 : kEdtInf;
+                if (p.h != nullptr) p.h[o + x] = edge ? 0 : kEdtInf;
             }
         }
 }
 
 struct EdtParams {
     const int* in;
+    const uint8_t* mask;  // first pass straight from a uint8 feature mask (in == nullptr)
     int* out;
     int* s;
     int* t;
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(128) edt_pass_kernel(const __grid_constant__ E
         if (p.axis == 0) o = l;
         else if (p.axis == 1) o = (l / p.n[2]) * sz + (l % p.n[2]);
         else o = l * p.n[2];
-        edt_line<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride);
+        if (p.mask != nullptr) edt_line_mask<long long>(p.mask + o, p.out + o, p.s + o, p.t + o, len, stride);
+        else edt_line<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride);
     }
 }
 
@@ -78,7 +80,7 @@ using namespace mss;
 
 extern "C" int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, const int32_t box_lo[3],
                               const int32_t box_hi[3], uint8_t* edges_out, int32_t* edt_input_out, void* stream) {
-    MSS_REQUIRE(labels && dims && box_lo && box_hi && edges_out && edt_input_out, MSS_E_ARG, "mask_edges: null argument");
+    MSS_REQUIRE(labels && dims && box_lo && box_hi && edges_out, MSS_E_ARG, "mask_edges: null argument");
     MSS_REQUIRE(cls >= 0 && cls <= 255, MSS_E_ARG, "mask_edges: class %d outside uint8", cls);
     EdgeParams p;
     for (int a = 0; a < 3; ++a) {
@@ -101,9 +103,10 @@ extern "C" int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int3
     return MSS_OK;
 }
 
-extern "C" int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
-                            int32_t axis, void* stream) {
-    MSS_REQUIRE(in && out && scratch_s && scratch_t && dims && in != out, MSS_E_ARG,
+static int edt_pass_impl(const int32_t* in, const uint8_t* mask, int32_t* out, int32_t* scratch_s, int32_t* scratch_t,
+                         const int32_t dims[3], int32_t axis, void* stream) {
+    MSS_REQUIRE((in != nullptr) != (mask != nullptr), MSS_E_ARG, "edt_pass: need exactly one input");
+    MSS_REQUIRE(out && scratch_s && scratch_t && dims && in != out, MSS_E_ARG,
                 "edt_pass: null argument (or in == out: the pass is not in place)");
     MSS_REQUIRE(axis >= 0 && axis < 3, MSS_E_ARG, "edt_pass: axis %d outside [0, 3)", axis);
     EdtParams p;
@@ -112,6 +115,7 @@ extern "C" int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s,
         p.n[a] = dims[a];
     }
     p.in = in;
+    p.mask = mask;
     p.out = out;
     p.s = scratch_s;
     p.t = scratch_t;
@@ -122,4 +126,16 @@ extern "C" int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s,
     edt_pass_kernel<<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
+}
+
+extern "C" int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
+                            int32_t axis, void* stream) {
+    MSS_REQUIRE(in != nullptr, MSS_E_ARG, "edt_pass: null argument");
+    return edt_pass_impl(in, nullptr, out, scratch_s, scratch_t, dims, axis, stream);
+}
+
+extern "C" int mss_edt_pass_mask(const uint8_t* mask, int32_t* out, int32_t* scratch_s, int32_t* scratch_t,
+                                 const int32_t dims[3], int32_t axis, void* stream) {
+    MSS_REQUIRE(mask != nullptr, MSS_E_ARG, "edt_pass_mask: null argument");
+    return edt_pass_impl(nullptr, mask, out, scratch_s, scratch_t, dims, axis, stream);
 }

@@ -30,32 +30,34 @@ def _bbox(mask: torch.Tensor) -> Optional[Tuple[Tuple[int, int, int], Tuple[int,
     return tuple(lo), tuple(hi)
 
 
-def _edges(labels: torch.Tensor, cls: int, lo, hi):
+def _edges(labels: torch.Tensor, cls: int, lo, hi) -> torch.Tensor:
     lib = _lib.load()
     n = tuple(h - l for l, h in zip(lo, hi))
     edges = torch.empty(n, dtype=torch.uint8, device=labels.device)
-    h0 = torch.empty(n, dtype=torch.int32, device=labels.device)
     rc = lib.mss_mask_edges(labels.data_ptr(), _lib.I3(*labels.shape), int(cls), _lib.I3(*lo), _lib.I3(*hi), edges.data_ptr(),
-                            h0.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                            None, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "mss_mask_edges")
-    return edges, h0
+    return edges
 
 
-def squared_edt(h0: torch.Tensor) -> torch.Tensor:
-    """Exact squared distance to the nearest voxel where ``h0 == 0`` (``h0``: int32, 2**29 elsewhere), returned in the
-    TRANSPOSED layout ``[D, W, H]``: the pass along the contiguous axis runs on a transposed copy so its line loop is
-    coalesced too."""
+def squared_edt(feature: torch.Tensor) -> torch.Tensor:
+    """Exact squared distance to the nearest non-zero voxel of the uint8 volume ``feature`` (int32; 2**29 when there is
+    none), returned in the TRANSPOSED layout ``[D, W, H]``: the pass along the contiguous axis runs on a transposed copy
+    so its line loop is coalesced too.  An int32 ``feature`` is taken as the transform's input itself (0 on features,
+    2**29 elsewhere)."""
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
-    d, h, w = h0.shape
-    t1, t2 = torch.empty_like(h0), torch.empty_like(h0)  # h0 itself is left untouched
-    s, t = torch.empty_like(h0), torch.empty_like(h0)
-    a = h0
-    for axis, b in ((0, t1), (1, t2)):
-        _lib.check(lib.mss_edt_pass(a.data_ptr(), b.data_ptr(), s.data_ptr(), t.data_ptr(), _lib.I3(d, h, w), axis, stream),
-                   "mss_edt_pass")
-        a = b
-    at = a.transpose(1, 2).contiguous()  # [D, W, H]
+    d, h, w = feature.shape
+    t1 = torch.empty((d, h, w), dtype=torch.int32, device=feature.device)
+    t2, s, t = torch.empty_like(t1), torch.empty_like(t1), torch.empty_like(t1)
+    dims = _lib.I3(d, h, w)
+    if feature.dtype == torch.uint8:
+        rc = lib.mss_edt_pass_mask(feature.contiguous().data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 0, stream)
+    else:
+        rc = lib.mss_edt_pass(feature.contiguous().data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 0, stream)
+    _lib.check(rc, "mss_edt_pass")
+    _lib.check(lib.mss_edt_pass(t1.data_ptr(), t2.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 1, stream), "mss_edt_pass")
+    at = t2.transpose(1, 2).contiguous()  # [D, W, H]
     bt = torch.empty_like(at)
     _lib.check(lib.mss_edt_pass(at.data_ptr(), bt.data_ptr(), s.data_ptr(), t.data_ptr(), _lib.I3(d, w, h), 1, stream),
                "mss_edt_pass")
@@ -81,7 +83,7 @@ def _np_percentile(sorted_vals: torch.Tensor, q: float) -> float:
         return float(np.float64(b) - d * (1.0 - t)) if t >= 0.5 else float(np.float64(a) + d * t)
 
 
-def _percent_distance(edges_from: torch.Tensor, edges_to: torch.Tensor, h_to: torch.Tensor, percentile: Optional[float]) -> float:
+def _percent_distance(edges_from: torch.Tensor, edges_to: torch.Tensor, percentile: Optional[float]) -> float:
     """``compute_percent_hausdorff_distance(edges_from, edges_to)``: distances from the voxels of one surface to the other."""
     n_from, n_to = int(edges_from.sum()), int(edges_to.sum())
     inf = float("inf")
@@ -90,7 +92,7 @@ def _percent_distance(edges_from: torch.Tensor, edges_to: torch.Tensor, h_to: to
     elif n_from == 0:  # ... `if not np.any(seg_pred): return dis[seg_gt]` - infinities for the OTHER surface's voxels
         dist = torch.full((n_to,), inf, dtype=torch.float64, device=edges_from.device)
     else:
-        dt_t = squared_edt(h_to)                 # [D, W, H]
+        dt_t = squared_edt(edges_to)             # [D, W, H]
         dist = dt_t[edges_from.transpose(1, 2).bool()].to(torch.float64).sqrt()
     if dist.numel() == 0:
         return float("nan")                      # surface_distance.shape == (0,)
@@ -118,13 +120,13 @@ def hausdorff_distance(pred: torch.Tensor, label: torch.Tensor, n_classes: int, 
                 out.append(float("nan"))
                 continue
             lo, hi = box
-            ep, hp = _edges(p, c, lo, hi)
-            ey, hy = _edges(y, c, lo, hi)
-            d1 = _percent_distance(ep, ey, hy, percentile)
+            ep = _edges(p, c, lo, hi)
+            ey = _edges(y, c, lo, hi)
+            d1 = _percent_distance(ep, ey, percentile)
             if directed:
                 out.append(d1)
                 continue
-            d2 = _percent_distance(ey, ep, hp, percentile)
+            d2 = _percent_distance(ey, ep, percentile)
             out.append(max(d1, d2))               # Python's max, as the reference calls it (NaN handling included)
     return np.asarray(out, dtype=np.float64)
 

@@ -85,12 +85,11 @@ extern "C" void host_bitplanes_roundtrip(const uint8_t* in32, uint8_t* out32, un
 extern "C" void host_edt_squared(const uint8_t* feature, int d, int h, int w, int* out) {
     const long long n = static_cast<long long>(d) * h * w;
     std::vector<int> a(n), b(n), s(n), t(n);
-    for (long long i = 0; i < n; ++i) a[i] = feature[i] ? 0 : mss::kEdtInf;
-    // axis 0 (stride h*w), axis 1 (stride w), axis 2 (stride 1); in-place is not allowed, so ping-pong
+    // axis 0 (stride h*w) straight from the mask, axis 1 (stride w), axis 2 (stride 1); never in place, so ping-pong
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             const long long o = static_cast<long long>(y) * w + x;
-            mss::edt_line<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w);
+            mss::edt_line_mask<long long>(feature + o, b.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w);
         }
     for (int z = 0; z < d; ++z)
         for (int x = 0; x < w; ++x) {

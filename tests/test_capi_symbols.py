@@ -46,6 +46,7 @@ def test_argument_errors_are_reported_not_thrown():
     assert lib.mss_dice_ce_sums(None, 1, 1, 1, 1, 2, None, 0, 1, None, None) == -1
     assert lib.mss_mask_edges(None, _lib.I3(1, 1, 1), 0, _lib.I3(0, 0, 0), _lib.I3(1, 1, 1), None, None, None) == -1
     assert lib.mss_edt_pass(None, None, None, None, _lib.I3(1, 1, 1), 0, None) == -1
+    assert lib.mss_edt_pass_mask(None, None, None, None, _lib.I3(1, 1, 1), 0, None) == -1
     assert lib.mss_flip_copy(None, None, 1, _lib.I3(1, 1, 1), 0, None) == -1
     assert lib.mss_mirror_merge(None, None, 1, 1.0, None, 1, _lib.I3(1, 1, 1), None) == -1
     assert lib.mss_intensity_transform(None, None, 8, 2, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, None) == -1

@@ -388,6 +388,8 @@ def test_squared_edt_matches_scipy_and_properties():
         got = squared_edt(h0).transpose(1, 2).cpu().numpy()
         want = ndimage.distance_transform_edt(~feat)
         assert np.array_equal(np.sqrt(got.astype(np.float64)), want)
+        got8 = squared_edt(torch.from_numpy(feat.astype(np.uint8)).cuda()).transpose(1, 2).cpu().numpy()  # mask-direct first pass
+        assert np.array_equal(got8, got)
     # identical surfaces: Hausdorff distance 0 for every present class
     lab = torch.from_numpy(_blobby(rs, (30, 30, 30), 4)).cuda()
     assert np.array_equal(mss.hausdorff_distance(lab, lab, 4), np.zeros(4))
