@@ -73,3 +73,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_docs_state_the_real_entry_point_count():
+    n = len(declared_symbols())
+    for doc in ("DESIGN.md", "README.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        claimed = {int(m) for m in re.findall(r"(\d+) entry points", text)}
+        assert claimed == {n}, f"{doc} says {sorted(claimed)} entry points, include/mss_b200.h declares {n}"
