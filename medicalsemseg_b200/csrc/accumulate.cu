@@ -498,13 +498,10 @@ static void window_range_box(const mss_layout_t* lay, long long n0, long long n1
 template <typename LT, int KC, int S, int MINB>
 static cudaError_t launch_one(dim3 grid, cudaStream_t s, const AccParams& p) {
     constexpr size_t smem = acc_smem_bytes<LT, KC, S>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(accumulate_kernel<LT, KC, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // the opt-in is per device (context): set it on every launch - a process may stitch on several GPUs
+    cudaError_t e = cudaFuncSetAttribute(accumulate_kernel<LT, KC, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
     accumulate_kernel<LT, KC, S, MINB><<<grid, kAccThreads, smem, s>>>(p);
     return cudaGetLastError();
 }

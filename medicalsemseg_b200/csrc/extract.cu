@@ -335,24 +335,23 @@ extern "C" int mss_extract_patches(const float* volume, const int32_t vol_origin
         for (int i = lay->win_lo[2]; i < lay->win_hi[2]; ++i)
             if ((st[i] - vol_origin[2]) % 4 != 0) starts_aligned = false;
     }
-    const bool tma_ok = use_tma == 1 && vec_layout && starts_aligned && rw <= 256 && encode_tiled_fn() != nullptr;
+    // the box {rw, kTmaBoxH, kTmaBoxD, 1} must fit the patch tensor; a failed descriptor encode (driver / shape the
+    // driver rejects) falls through to the shifted-vector kernel, which serves the same layout
+    bool tma_ok = use_tma == 1 && vec_layout && starts_aligned && rw <= 256 && p.g.roi[1] >= kTmaBoxH &&
+                  p.g.roi[0] >= kTmaBoxD && encode_tiled_fn() != nullptr;
+    CUtensorMap in_map, out_map;
     if (tma_ok) {
-        CUtensorMap in_map, out_map;
         const long long in_dims[4] = {vol_extent[2], vol_extent[1], vol_extent[0],
                                       static_cast<long long>(p.g.nb) * n_channels};
         const long long out_dims[4] = {rw, p.g.roi[1], p.g.roi[0], static_cast<long long>(n_windows) * n_channels};
         const int box[4] = {rw, kTmaBoxH, kTmaBoxD, 1};
-        rc = encode_map(&in_map, volume, in_dims, box);
-        if (rc != MSS_OK) return rc;
-        rc = encode_map(&out_map, patches_out, out_dims, box);
-        if (rc != MSS_OK) return rc;
+        if (encode_map(&in_map, volume, in_dims, box) != MSS_OK || encode_map(&out_map, patches_out, out_dims, box) != MSS_OK)
+            tma_ok = false;
+    }
+    if (tma_ok) {
         const int stage_bytes = rw * kTmaBoxH * kTmaBoxD * 4;
         const size_t smem = static_cast<size_t>(stage_bytes) * kTmaStages;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MSS_CUDA(cudaFuncSetAttribute(extract_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        MSS_CUDA(cudaFuncSetAttribute(extract_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  // per device
         const long long n_tiles = static_cast<long long>(n_windows) * n_channels * ((p.g.roi[0] + kTmaBoxD - 1) / kTmaBoxD) *
                                   ((p.g.roi[1] + kTmaBoxH - 1) / kTmaBoxH);
         int ctas_per_sm = static_cast<int>((200 * 1024) / (smem + 1024));

@@ -289,11 +289,7 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
         p.rows_per_block = static_cast<int>(per_block);
         const long long blocks = (n_rows + per_block - 1) / per_block;
         const size_t smem = static_cast<size_t>(pass_rows) * p.slot_pitch;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MSS_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
-            attr_set = true;
-        }
+        MSS_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));  // per device
         resample_rows_kernel<<<static_cast<unsigned>(blocks), 256, smem, s>>>(p);
     } else {
         p.rows_per_block = 0;

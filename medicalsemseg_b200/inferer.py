@@ -24,7 +24,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .grid import PAD_MODES, WindowGrid, _option, make_grid
+from .grid import PAD_MODES, WindowGrid, _option, fall_back_roi, make_grid
 from .importance import importance_map as build_importance_map
 
 _DTYPES = {torch.float32: _lib.MSS_F32, torch.float16: _lib.MSS_F16, torch.bfloat16: _lib.MSS_BF16}
@@ -126,8 +126,8 @@ _PLAN_CACHE: Dict[Any, StitchPlan] = {}
 
 
 def get_plan(spatial: Sequence[int], roi_size: Any, overlap: float, device: torch.device, n_volumes: int) -> StitchPlan:
-    roi_key = tuple(roi_size) if isinstance(roi_size, (list, tuple)) else roi_size
-    key = (tuple(spatial), roi_key, float(overlap), str(device), n_volumes)
+    roi_key = fall_back_roi(roi_size, spatial)  # always a tuple of ints (roi_size may be a scalar, list or ndarray)
+    key = (tuple(int(v) for v in spatial), roi_key, float(overlap), str(device), n_volumes)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         plan = StitchPlan(make_grid(spatial, roi_size, overlap), device, n_volumes)

@@ -75,8 +75,13 @@ def dice_from_counts(counts: Any) -> np.ndarray:
 
 
 class DiceMeter:
-    """Per-volume Dice bookkeeping of engine/test.py:56-69: one ``[K]`` Dice vector per volume, class mean =
-    nanmean over volumes (NaN if the class never occurs), mDice = nanmean over classes."""
+    """Per-volume Dice bookkeeping of ``eval_model`` (engine/test.py:37-94): the loader yields one volume per iteration,
+    each iteration feeds its per-class Dice (NaN classes skipped, utils/misc.py:96) and ``mDice = nanmean`` over that
+    volume's classes into ``MetricLogger`` meters, and the reported values are the meters' global averages.  Hence
+
+    * class mean = mean over the volumes in which the class occurs (NaN if it never does);
+    * ``mDice``  = mean over VOLUMES of the per-volume nanmean over classes - not the nanmean of the class means
+      (A = (1.0, 0.5), B = (0.8, nan) gives 0.775, not 0.70)."""
 
     def __init__(self, n_classes: int) -> None:
         self.k = n_classes
@@ -97,15 +102,27 @@ class DiceMeter:
         c = counts.detach().cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)
         self.per_volume.extend(list(c.reshape(-1, 3, self.k)))
 
+    def per_volume_dice(self) -> np.ndarray:
+        return np.stack([dice_from_counts(c) for c in self.per_volume]) if self.per_volume else np.full((0, self.k), np.nan)
+
     def class_means(self) -> Tuple[np.ndarray, float]:
-        d = np.stack([dice_from_counts(c) for c in self.per_volume]) if self.per_volume else np.full((1, self.k), np.nan)
+        """``(eval/class{c}Dice for every c, eval/mDice)`` as ``eval_model`` would log them for the volumes seen so far."""
+        d = self.per_volume_dice()
         means = np.full(self.k, np.nan)
+        if d.shape[0] == 0:
+            return means, float("nan")
+        seen = ~np.isnan(d)
         for c in range(self.k):
-            col = d[:, c]
-            if np.any(~np.isnan(col)):
-                means[c] = np.nanmean(col)
-        m = float(np.nanmean(means)) if np.any(~np.isnan(means)) else float("nan")
-        return means, m
+            if seen[:, c].any():
+                means[c] = d[seen[:, c], c].mean()
+        # per-volume mDice (engine/test.py:70); a volume with no class at all contributes NaN, as the reference's meter would
+        per_vol = np.array([v[s].mean() if s.any() else np.nan for v, s in zip(d, seen)])
+        return means, float(per_vol.mean())
+
+    def mean_of_class_means(self) -> float:
+        """nanmean over classes of the class means (NOT what the reference logs; kept for set-level summaries)."""
+        means, _ = self.class_means()
+        return float(np.nanmean(means)) if np.any(~np.isnan(means)) else float("nan")
 
 
 def gather_volume_counts(counts: Any, group: Any = None) -> np.ndarray:

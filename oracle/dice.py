@@ -65,3 +65,26 @@ def class_means(dice_scores: np.ndarray) -> Tuple[np.ndarray, float]:
             means[c] = np.nanmean(col)
     m = float(np.nanmean(means)) if np.any(~np.isnan(means)) else float("nan")
     return means, m
+
+
+def eval_meters(per_volume_dice: np.ndarray) -> Tuple[np.ndarray, float]:
+    """What ``eval_model`` reports for a SET of volumes (engine/test.py:37-94 with ``utils/misc.py:93-100,16-60``): the loader
+    yields one volume per iteration; each iteration computes ``class_means`` of that single volume, feeds every class value
+    that is not ``np.nan`` to the meter ``class{c}Dice`` and ``mDice = nanmean`` over that volume's classes to the meter
+    ``mDice``; the result is every meter's ``global_avg`` (sum / count).  So ``eval/mDice`` is the mean over volumes of
+    the per-volume class mean, NOT the mean over classes of the per-class means.  ``per_volume_dice`` is ``[N, K]``."""
+    d = np.asarray(per_volume_dice, dtype=np.float64)
+    k = d.shape[1]
+    tot, cnt = np.zeros(k), np.zeros(k)
+    m_tot, m_cnt = 0.0, 0
+    for vol in d:
+        means, m = class_means(vol[None])
+        for c in range(k):
+            if not np.isnan(means[c]):  # `v is np.nan` is skipped by MetricLogger.update (utils/misc.py:96)
+                tot[c] += means[c]
+                cnt[c] += 1
+        m_tot += m          # a tensor .item() NaN is not the np.nan object: it would be added (and poison the mean)
+        m_cnt += 1
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cls = np.where(cnt > 0, tot / np.maximum(cnt, 1), np.nan)
+    return cls, (m_tot / m_cnt if m_cnt else float("nan"))

@@ -4,7 +4,8 @@
 * ``compute_steps``        :274-298  `_compute_steps_for_sliding_window`
 * ``get_gaussian``         :258-271  `_get_gaussian` (scipy.ndimage.gaussian_filter, as the reference calls it)
 * ``mirror_and_pred``      :511-568  `_internal_maybe_mirror_and_pred_3D`
-* ``predict_3D_tiled``     :300-437  `_internal_predict_3D_3Dconv_tiled`, the float32 (`all_in_gpu=False`) branch
+* ``predict_3D_tiled``     :300-437  `_internal_predict_3D_3Dconv_tiled`: the float32 (`all_in_gpu=False`) branch and the
+                                     half-precision `all_in_gpu=True` branch (:346-372, :399-400, :420-431)
 
 Pinned against outputs of those very methods (tests/golden/nnunet_*.npz; make_golden.py imports the reference module
 with stand-ins for its absent third-party imports and runs it on the CPU).  ``pad_nd_image`` (batchgenerators, absent
@@ -78,7 +79,7 @@ def pad_to_patch(x: np.ndarray, patch_size: Sequence[int]) -> Tuple[np.ndarray, 
 
 def predict_3D_tiled(x: np.ndarray, network: Callable, nonlin: Callable, num_classes: int, patch_size: Sequence[int],
                      step_size: float = 0.5, do_mirroring: bool = True, mirror_axes: Sequence[int] = (0, 1, 2),
-                     use_gaussian: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+                     use_gaussian: bool = True, all_in_gpu: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     data, slicer = pad_to_patch(x, patch_size)
     steps = compute_steps(patch_size, data.shape[1:], step_size)
     num_tiles = len(steps[0]) * len(steps[1]) * len(steps[2])
@@ -89,6 +90,29 @@ def predict_3D_tiled(x: np.ndarray, network: Callable, nonlin: Callable, num_cla
     else:
         mult = None
         add_nb = np.ones(data.shape[1:], dtype=np.float32)
+    if all_in_gpu:
+        # :346-372 - the importance map, the aggregated results and the aggregated counts are HALF tensors; every `+=` on
+        # them computes in float32 and rounds the sum to half (torch type promotion for in-place ops on a half tensor)
+        if mult is not None:
+            mult = mult.half()
+            mult[mult == 0] = mult[mult != 0].min()
+            add_t = mult
+        else:
+            add_t = torch.ones(data.shape[1:])
+        agg_t = torch.zeros([num_classes] + list(data.shape[1:]), dtype=torch.half)
+        nb_t = torch.zeros([num_classes] + list(data.shape[1:]), dtype=torch.half)
+        data_t = torch.from_numpy(np.ascontiguousarray(data))
+        for sx in steps[0]:
+            for sy in steps[1]:
+                for sz in steps[2]:
+                    sl = (slice(None), slice(sx, sx + patch_size[0]), slice(sy, sy + patch_size[1]), slice(sz, sz + patch_size[2]))
+                    pred = mirror_and_pred(data_t[sl][None], network, nonlin, num_classes, mirror_axes, do_mirroring, mult)[0]
+                    agg_t[sl] += pred.half()   # :399-400, :405
+                    nb_t[sl] += add_t          # :406
+        agg_t = agg_t[(slice(None),) + slicer]
+        nb_t = nb_t[(slice(None),) + slicer]
+        probs_t = agg_t / nb_t                 # half / half -> half (:420)
+        return probs_t.argmax(0).numpy(), probs_t.numpy()
     agg = np.zeros([num_classes] + list(data.shape[1:]), dtype=np.float32)
     nb = np.zeros([num_classes] + list(data.shape[1:]), dtype=np.float32)
     for sx in steps[0]:

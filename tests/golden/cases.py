@@ -30,6 +30,19 @@ SW_CASES = {
     "cfg1_geometry": dict(shape=[1, 1, 128, 128, 128], roi=[96, 96, 96], overlap=0.25, mode="gaussian", sw_batch=4, k=14, seed=10),
 }
 
+# BASELINE.json configs at their REAL geometry: the reference's engine/utils.py is run on them once in
+# the build container (minutes, gigabytes); fixtures hold sha256 of the full logits / labels plus a strided sample.
+#   cfg2: 512x512x200, K=14, 400 windows (starts ... 384, 416 | 0, 48, 96, 104)
+#   cfg4: 4-channel 240x240x155, K=3, 48 windows (starts 0, 48, 96, 144 | 0, 48, 59: unaligned clamped start, odd W)
+#   cfg3: 512x512x1024, 2100 windows (z starts ... 912, 928); K cut to 2 so the reference's K-replicated count map fits
+FULLSIZE_SW_CASES = {
+    "cfg2_geometry": dict(shape=[1, 1, 512, 512, 200], roi=[96, 96, 96], overlap=0.5, mode="gaussian", sw_batch=4, k=14, seed=11),
+    "cfg4_geometry": dict(shape=[1, 4, 240, 240, 155], roi=[96, 96, 96], overlap=0.5, mode="gaussian", sw_batch=4, k=3, seed=12),
+    "cfg3_geometry_k2": dict(shape=[1, 1, 512, 512, 1024], roi=[96, 96, 96], overlap=0.5, mode="gaussian", sw_batch=4, k=2, seed=13),
+}
+FULLSIZE_SAMPLE_STRIDE = 99991   # prime; logits sample
+FULLSIZE_LABEL_STRIDE = 9973
+
 VOTE_CASES = {
     "k3_m5": dict(shape=[24, 20, 31], k=3, m=5, seed=21),        # BraTS ensemble shape class (cfg4: K=3, M=5)
     "k14_m5": dict(shape=[17, 23, 29], k=14, m=5, seed=22),
@@ -99,6 +112,13 @@ NNUNET_CASES = {
     "no_mirror": dict(shape=[1, 33, 35, 38], patch=[16, 16, 16], step=0.75, mirror=False, axes=(0, 1, 2), gaussian=True, k=3, seed=53),
     "padded_single_tile": dict(shape=[1, 10, 14, 16], patch=[16, 16, 16], step=0.5, mirror=True, axes=(0, 1, 2), gaussian=True, k=2, seed=54),
     "fine_steps": dict(shape=[1, 30, 30, 30], patch=[16, 16, 16], step=0.3, mirror=True, axes=(1,), gaussian=True, k=3, seed=55),
+    # all_in_gpu=True (:349-356, :399-400, :420-431): half importance map, half aggregated results / counts, half division
+    "half_mirror_all": dict(shape=[1, 40, 36, 44], patch=[16, 16, 16], step=0.5, mirror=True, axes=(0, 1, 2), gaussian=True, k=3,
+                            seed=56, all_in_gpu=True),
+    "half_no_mirror_odd": dict(shape=[2, 33, 29, 35], patch=[16, 12, 20], step=0.4, mirror=False, axes=(0, 1, 2), gaussian=True,
+                               k=4, seed=57, all_in_gpu=True),
+    "half_single_tile": dict(shape=[1, 10, 14, 16], patch=[16, 16, 16], step=0.5, mirror=True, axes=(0, 2), gaussian=True, k=2,
+                             seed=58, all_in_gpu=True),
 }
 
 

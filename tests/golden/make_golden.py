@@ -3,7 +3,8 @@
 
 Run in the build container only (needs /root/reference; the GPU box does not have it):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                      # everything (the full-size cases need ~25 GB RAM, minutes)
+    python tests/golden/make_golden.py --sections fullsize  # one section, merged into the existing manifest.json
 
 * ``engine/utils.py::sliding_window_inference`` is imported from ``/root/reference`` and
   executed VERBATIM on CPU; its MONAI imports (engine/utils.py:5-13) are served by
@@ -35,8 +36,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "monai_shim"))
 sys.path.insert(0, REF)
 
 from oracle.predictors import ArithmeticPredictor  # noqa: E402
-from tests.golden.cases import (INTENSITY_CASES, NNUNET_CASES, RESAMPLE_CASES, SW_CASES, VOTE_CASES,  # noqa: E402
-                                make_ct_volume, make_label_map, make_nnunet_volume, make_volume, make_vote_maps)
+from tests.golden.cases import (FULLSIZE_LABEL_STRIDE, FULLSIZE_SAMPLE_STRIDE, FULLSIZE_SW_CASES, INTENSITY_CASES,  # noqa: E402
+                                NNUNET_CASES, RESAMPLE_CASES, SW_CASES, VOTE_CASES, make_ct_volume, make_label_map,
+                                make_nnunet_volume, make_volume, make_vote_maps)
 
 
 def sha(a: np.ndarray) -> str:
@@ -141,11 +143,12 @@ def load_reference_segmentation_network():
     return mod
 
 
-def main() -> None:
-    torch.set_num_threads(os.cpu_count() or 1)
+SECTIONS = ("sliding_window", "fullsize", "vote", "resample", "intensity", "nnunet", "importance_map")
+
+
+def run_sliding_window(manifest: dict) -> None:
     from engine.utils import sliding_window_inference as ref_swi  # the reference itself
 
-    manifest = {"sliding_window": {}, "vote": {}, "importance_map": {}, "resample": {}, "intensity": {}, "nnunet": {}}
     for name, c in SW_CASES.items():
         vol = torch.from_numpy(make_volume(c))
         pred = ArithmeticPredictor(c["k"])
@@ -173,6 +176,52 @@ def main() -> None:
         manifest["sliding_window"][name] = entry
         print(name, entry["shape"], entry["sha256"][:12], len(pred.calls), "predictor calls")
 
+
+def run_fullsize(manifest: dict) -> None:
+    """BASELINE.json configs[1], [2] (K=2) and [3] at their real geometry through the reference's own engine/utils.py:19-159,
+    then the reference's own post-processing (engine/test.py:140-141).  Stored: sha256 of the full fp32 logits and uint8
+    labels, strided samples, the count of voxels whose softmax-argmax differs from the plain argmax of the logits (softmax
+    rounding can merge a near-tie), and the number of predictor calls."""
+    import time
+
+    from engine.utils import sliding_window_inference as ref_swi
+
+    for name, c in FULLSIZE_SW_CASES.items():
+        t0 = time.time()
+        vol = torch.from_numpy(make_volume(c))
+        pred = ArithmeticPredictor(c["k"])
+        affine = torch.tensor([[1.5, 1.5, 2.0]] * c["shape"][0], dtype=torch.float32)
+        with torch.no_grad():
+            out = ref_swi(
+                inputs=vol, affine=affine, roi_size=c["roi"], sw_batch_size=c["sw_batch"], predictor=pred,
+                overlap=c["overlap"], mode=c["mode"], cval=c.get("cval", 0.0), device="cpu", sw_device="cpu",
+            )
+        out_np = out.contiguous().numpy()
+        probs = torch.softmax(out, 1).cpu().numpy()  # engine/test.py:140
+        labels = np.argmax(probs, axis=1).astype(np.uint8)[0]  # engine/test.py:141
+        del probs
+        plain = np.argmax(out_np, axis=1).astype(np.uint8)[0]
+        top2 = np.sort(np.partition(out_np[0], -2, axis=0)[-2:], axis=0)
+        gap = (top2[1] - top2[0]) / np.maximum(np.abs(top2[1]), 1e-30)
+        entry = {
+            "shape": list(out_np.shape), "sha256": sha(out_np), "labels_sha256": sha(labels),
+            "labels_plain_argmax_sha256": sha(plain), "softmax_vs_plain_argmax_mismatch": int((plain != labels).sum()),
+            "near_ties_1e-5": int((gap < 1e-5).sum()), "n_predictor_calls": len(pred.calls),
+            "sample_stride": FULLSIZE_SAMPLE_STRIDE, "label_stride": FULLSIZE_LABEL_STRIDE, "stored": "sample",
+            "seconds_on_cpu": round(time.time() - t0, 1), "cpu_threads": torch.get_num_threads(),
+        }
+        # the voxels where softmax->argmax (the reference) and the plain argmax disagree are stored so the GPU test can allow
+        # exactly those (at most a handful)
+        diff_idx = np.flatnonzero(plain.reshape(-1) != labels.reshape(-1)).astype(np.int64)
+        np.savez_compressed(os.path.join(HERE, f"sw_{name}.npz"), sample=out_np.reshape(-1)[::FULLSIZE_SAMPLE_STRIDE].copy(),
+                            labels_sample=labels.reshape(-1)[::FULLSIZE_LABEL_STRIDE].copy(), softmax_diff_index=diff_idx,
+                            softmax_diff_label=labels.reshape(-1)[diff_idx].copy())
+        manifest["fullsize"][name] = entry
+        print(name, entry)
+        del out, out_np, labels, plain, top2, gap, vol
+
+
+def run_vote(manifest: dict) -> None:
     get_class_votes, get_new_label = load_reference_vote()
     for name, c in VOTE_CASES.items():
         maps = make_vote_maps(c)
@@ -183,6 +232,8 @@ def main() -> None:
         manifest["vote"][name] = {"sha256": sha(new), "shape": list(new.shape)}
         print("vote", name, new.shape, sha(new)[:12])
 
+
+def run_resample(manifest: dict) -> None:
     ref_resample = load_reference_resample()
     for name, c in RESAMPLE_CASES.items():
         img = make_label_map(c)
@@ -192,6 +243,8 @@ def main() -> None:
             bool((np.take(out, -1, axis=a) == 0).all()) for a in range(3)]}
         print("resample", name, out.shape, sha(out)[:12])
 
+
+def run_intensity(manifest: dict) -> None:
     scaler_cls = load_reference_cubed_scaler()
     for name, c in INTENSITY_CASES.items():
         vol = make_ct_volume(c)
@@ -201,19 +254,22 @@ def main() -> None:
                                        "min": float(out.min()), "max": float(out.max())}
         print("intensity", name, out.shape, out.dtype, sha(out)[:12])
 
+
+def run_nnunet(manifest: dict) -> None:
     from oracle.predictors import PositionalPredictor
     nn_mod = load_reference_segmentation_network()
 
     class RefNet(nn_mod.SegmentationNetwork):
-        def __init__(self, k, patch):
+        def __init__(self, k, patch, device=0):
             super().__init__()
             self.num_classes = k
             self.conv_op = torch.nn.Conv3d
             self.inference_apply_nonlin = lambda t: t
             self.pred = PositionalPredictor(k, patch)
+            self._device = device
 
         def get_device(self):
-            return 0
+            return self._device
 
         def forward(self, t):
             return self.pred(t)
@@ -223,24 +279,31 @@ def main() -> None:
     try:
         for name, c in NNUNET_CASES.items():
             vol = make_nnunet_volume(c)
-            net = RefNet(c["k"], c["patch"])
+            half = bool(c.get("all_in_gpu", False))
+            # all_in_gpu allocates with device=self.get_device() (:352-365): a torch.device("cpu") keeps the reference's
+            # `get_device() != "cpu"` assertion true (a torch.device never equals a str) and its half-precision branch on the CPU
+            net = RefNet(c["k"], c["patch"], torch.device("cpu") if half else 0)
             with torch.no_grad():
                 seg, probs = net._internal_predict_3D_3Dconv_tiled(
                     vol, c["step"], c["mirror"], tuple(c["axes"]), tuple(c["patch"]), None, c["gaussian"], "constant",
-                    {"constant_values": 0}, False, False)
+                    {"constant_values": 0}, half, False)
+            if half:
+                assert probs.dtype == np.float16, probs.dtype
             np.savez_compressed(os.path.join(HERE, f"nnunet_{name}.npz"), seg=seg.astype(np.uint8),
                                 probs=probs.astype(np.float32))
             manifest["nnunet"][name] = {"sha256_probs": sha(probs.astype(np.float32)), "sha256_seg": sha(seg.astype(np.uint8)),
-                                        "shape": list(probs.shape),
+                                        "shape": list(probs.shape), "probs_dtype_in_reference": str(probs.dtype),
                                         "steps": nn_mod.SegmentationNetwork._compute_steps_for_sliding_window(
                                             tuple(c["patch"]), tuple(max(a, b) for a, b in zip(c["shape"][1:], c["patch"])), c["step"])}
-            print("nnunet", name, probs.shape, sha(probs.astype(np.float32))[:12])
+            print("nnunet", name, probs.shape, probs.dtype, sha(probs.astype(np.float32))[:12])
         for ps in [(96, 96, 96), (16, 16, 16), (16, 12, 20)]:
             g = nn_mod.SegmentationNetwork._get_gaussian(ps, sigma_scale=1.0 / 8)
             manifest["nnunet"]["gaussian_" + "x".join(map(str, ps))] = {"sha256": sha(g), "min": float(g.min())}
     finally:
         torch.Tensor.cuda = real_cuda
 
+
+def run_importance_map(manifest: dict) -> None:
     # importance maps as the shimmed MONAI-0.8 restatement produces them (unpinned, recorded for drift detection)
     from oracle.monai08 import compute_importance_map
     for roi in [(96, 96, 96), (16, 16, 16), (24, 16, 32), (8, 12, 20)]:
@@ -251,9 +314,23 @@ def main() -> None:
             "axis0_profile_head": [float(v) for v in m[:3, roi[1] // 2, roi[2] // 2]],
             "axis0_profile_tail": [float(v) for v in m[-2:, roi[1] // 2, roi[2] // 2]],
         }
-    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+
+
+def main() -> None:
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sections", nargs="*", default=list(SECTIONS), choices=SECTIONS)
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    path = os.path.join(HERE, "manifest.json")
+    manifest = json.load(open(path)) if os.path.exists(path) else {}
+    for sec in args.sections:
+        manifest[sec] = {}
+        globals()["run_" + sec](manifest)
+    with open(path, "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
-    print("wrote", os.path.join(HERE, "manifest.json"))
+    print("wrote", path)
 
 
 if __name__ == "__main__":

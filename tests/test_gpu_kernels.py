@@ -118,7 +118,7 @@ def test_dice_meter_follows_reference_nan_rules():
     meter.update(pred, lab)
     meter.update(pred, lab)
     means, m = meter.class_means()
-    want, want_m = odice.class_means(np.stack([odice.dice_from_counts(odice.dice_counts(pred.cpu().numpy(), lab.cpu().numpy(), k))] * 2))
+    want, want_m = odice.eval_meters(np.stack([odice.dice_from_counts(odice.dice_counts(pred.cpu().numpy(), lab.cpu().numpy(), k))] * 2))
     assert np.allclose(means, want, equal_nan=True) and m == pytest.approx(want_m)
     assert np.isnan(means[3])
 

@@ -136,8 +136,10 @@ def test_nnunet_tiler_matches_reference_run(name):
     vol = make_nnunet_volume(c)
     with torch.no_grad():
         seg, probs = onnunet.predict_3D_tiled(vol, PositionalPredictor(c["k"], c["patch"]), lambda t: t, c["k"], c["patch"],
-                                              c["step"], c["mirror"], tuple(c["axes"]), c["gaussian"])
-    assert np.array_equal(probs, fx["probs"]) and np.array_equal(seg.astype(np.uint8), fx["seg"])
+                                              c["step"], c["mirror"], tuple(c["axes"]), c["gaussian"],
+                                              all_in_gpu=c.get("all_in_gpu", False))
+    assert str(probs.dtype) == meta["probs_dtype_in_reference"]
+    assert np.array_equal(probs.astype(np.float32), fx["probs"]) and np.array_equal(seg.astype(np.uint8), fx["seg"])
     image = tuple(max(a, b) for a, b in zip(c["shape"][1:], c["patch"]))
     assert onnunet.compute_steps(c["patch"], image, c["step"]) == meta["steps"]
 

@@ -92,3 +92,30 @@ def test_dice_counts_and_nan_rules():
         logits[p, 0, 0, i] = 1.0
     md = odice.monai_meandice(logits, torch.from_numpy(lab.astype(np.float32)).reshape(1, 1, 1, 6), 4)
     assert np.allclose(md.numpy()[0, :3], d[:3]) and np.isnan(md.numpy()[0, 3])
+
+
+def test_eval_meters_mdice_is_the_mean_over_volumes_of_the_per_volume_class_mean():
+    """engine/test.py:59-76 + utils/misc.py:93-100: mDice is logged per iteration (one volume) and averaged by the meter.
+    A = (1.0, 0.5), B = (0.8, nan): the reference reports (0.75 + 0.8) / 2 = 0.775, not nanmean((0.9, 0.5)) = 0.70."""
+    from medicalsemseg_b200.metrics import DiceMeter
+
+    d = np.array([[1.0, 0.5], [0.8, np.nan]])
+    cls, m = odice.eval_meters(d)
+    assert cls.tolist() == [0.9, 0.5] and m == pytest.approx(0.775)
+    # the product's meter, fed exact counts that produce those Dice values: TP, P, Y per class
+    a = np.array([[5, 1], [5, 2], [5, 2]], dtype=np.int64)       # dice (1.0, 0.5)
+    b = np.array([[4, 0], [5, 3], [5, 0]], dtype=np.int64)       # dice (0.8, nan: class 1 absent from the label)
+    meter = DiceMeter(2)
+    meter.add_counts(np.stack([a, b]))
+    means, mm = meter.class_means()
+    assert np.allclose(means, cls) and mm == pytest.approx(m)
+    assert meter.mean_of_class_means() == pytest.approx(0.70)
+    rs = np.random.RandomState(3)
+    counts = rs.randint(0, 50, size=(7, 3, 5)).astype(np.int64)
+    counts[:, 2, 3] = 0           # class 3 never occurs
+    counts[2:5, 2, 1] = 0         # class 1 missing from three volumes
+    meter = DiceMeter(5)
+    meter.add_counts(counts)
+    means, mm = meter.class_means()
+    want, want_m = odice.eval_meters(np.stack([odice.dice_from_counts(c) for c in counts]))
+    assert np.allclose(means, want, equal_nan=True) and mm == pytest.approx(want_m) and np.isnan(means[3])
