@@ -27,6 +27,8 @@ SHAPES = {
     "btcv": dict(shape=(1, 1, 512, 512, 200), k=14, m=5),
     "brats": dict(shape=(1, 4, 240, 240, 155), k=3, m=5),
     "small": dict(shape=(1, 1, 192, 192, 200), k=14, m=5),
+    "btcv_k3": dict(shape=(1, 1, 512, 512, 200), k=3, m=5),      # diagnostics: few classes on a large aligned volume
+    "brats_w156": dict(shape=(1, 4, 240, 240, 156), k=3, m=5),   # diagnostics: BraTS with 16-byte aligned window starts
     "wholebody": dict(shape=(1, 1, 512, 512, 1024), k=14, m=5),  # label-map kernels only (--only vote,dice)
 }
 

@@ -35,7 +35,7 @@ extern "C" {
 #define MSS_E_DRIVER (-4)      /* CUDA driver entry point (tensor-map encode) unavailable            */
 
 #define MSS_MAX_CLASSES 32       /* K for the fused label path; accumulate itself takes any K      */
-#define MSS_MAX_BATCH_PTRS 128   /* predictor batches per mss_accumulate call                      */
+#define MSS_MAX_BATCH_PTRS 640   /* predictor batches per mss_accumulate call                      */
 #define MSS_MAX_VOTE_MAPS 15     /* ensemble size M (4-bit vote counters)                          */
 #define MSS_MAX_VOTE_CLASSES 16
 
@@ -143,6 +143,16 @@ int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32
                    int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
                    const float* importance_map, float* acc, int32_t fuse, uint8_t* labels,
                    int32_t label_pitch_w, float tie_tol, unsigned long long* near_ties, void* stream);
+
+/* The raw-sum form of mss_accumulate for a buffer whose window box is SHARED with other ranks (multi-GPU: the window
+ * list of engine/utils.py:120-125 is cut into one contiguous range per rank): only windows [own_first, own_first +
+ * own_count) of the box exist for this buffer, the others are ignored entirely.  Always MSS_FUSE_NONE: acc receives
+ * raw weighted sums of this rank's windows (voxels none of them covers are not written - clear the buffer first).
+ * [first_window, +n_windows) must lie inside the owned range. */
+int mss_accumulate_range(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches,
+                         int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
+                         int64_t own_first, int64_t own_count, const float* importance_map, float* acc,
+                         void* stream);
 
 /* Normalise + softmax-argmax -> uint8 (engine/utils.py:151 + engine/test.py:140-141) over the local
  * box [box_lo, box_hi) of `logits[Nb, K, extent_d, extent_h, pitch_w]`.  normalise != 0 divides by

@@ -18,7 +18,7 @@ BLEND_CONSTANT, BLEND_PROFILES = 0, 1
 GAUSS_MONAI08_ERF, GAUSS_MONAI12_EXP = 0, 1
 FUSE_NONE, FUSE_LOGITS, FUSE_LABELS = 0, 1, 2
 INT_CBRT, INT_SCALE, INT_RESCALE, INT_CLIP_LO, INT_CLIP_HI, INT_NORM, INT_NONZERO, INT_F64 = 1, 2, 4, 8, 16, 32, 64, 128
-MAX_BATCH_PTRS = 128
+MAX_BATCH_PTRS = 640
 MAX_VOTE_MAPS = 15
 MAX_VOTE_CLASSES = 16
 MAX_DICE_CLASSES = 16
@@ -49,6 +49,8 @@ _SIGNATURES = {
     "mss_extract_patches": (C.c_int, [vp, I3, I3, c_i32, c_f32, C.POINTER(Layout), c_i64, c_i32, vp, vp, c_i32, vp]),
     "mss_accumulate": (C.c_int, [C.POINTER(Layout), C.POINTER(vp), c_i32, c_i32, c_i32, c_i64, c_i64, vp, vp, c_i32,
                                  vp, c_i32, c_f32, vp, vp]),
+    "mss_accumulate_range": (C.c_int, [C.POINTER(Layout), C.POINTER(vp), c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, vp,
+                                       vp, vp]),
     "mss_finalize_labels": (C.c_int, [C.POINTER(Layout), vp, vp, c_i32, I3, I3, vp, c_i32, vp, vp, c_f32, vp, vp]),
     "mss_majority_vote": (C.c_int, [C.POINTER(vp), c_i32, c_i32, c_i64, vp, vp]),
     "mss_dice_counts": (C.c_int, [vp, vp, c_i32, c_i64, c_i32, vp, vp]),

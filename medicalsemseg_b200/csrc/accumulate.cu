@@ -12,142 +12,9 @@
 // only if a window of an earlier launch touched the voxel (no memset needed) and written once; a voxel
 // whose last covering window is in this launch is finished on the spot (divide by the weight count, or
 // argmax straight to uint8) and never travels through HBM again.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
-#include <cstdlib>
-#include <type_traits>
-
-#include "common.cuh"
-#include "labels.cuh"
+#include "acc_common.cuh"
 
 namespace mss {
-
-constexpr int kAccThreads = 128;
-constexpr int kMaxCand = 64;  // windows listed per shared-memory chunk
-
-struct AccParams {
-    Geo g;
-    const void* batch[MSS_MAX_BATCH_PTRS];
-    int sw_batch;
-    long long g0, g1;  // owned-window range of this call, over n_volumes * n_local
-    const float* imp;
-    float* acc;
-    uint8_t* labels;
-    int label_pitch;
-    int fuse;
-    float tie_tol;
-    unsigned long long* near_ties;
-    int box_lo[3];  // local box this launch covers; box_lo[2] is a multiple of 4
-    int box_n[3];
-    int nq;        // quads per row of the box
-    int tq, th;    // tile: quads per row, rows
-    int n_wtiles;  // tiles along W
-    int b_lo;      // first volume touched
-    int vec_ok;    // logits pointers and roi allow 16-byte (8-byte for 16-bit logits) vector loads
-};
-
-template <typename LT>
-struct LogitLoad;
-template <>
-struct LogitLoad<float> {
-    static __device__ __forceinline__ float4 quad(const float* p) { return ld_stream_f4(p); }
-    static __device__ __forceinline__ float one(const float* p) { return __ldg(p); }
-};
-template <>
-struct LogitLoad<__half> {
-    static __device__ __forceinline__ float4 quad(const __half* p) {
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-        return make_float4(a.x, a.y, b.x, b.y);
-    }
-    static __device__ __forceinline__ float one(const __half* p) { return __half2float(__ldg(p)); }
-};
-template <>
-struct LogitLoad<__nv_bfloat16> {
-    static __device__ __forceinline__ float4 quad(const __nv_bfloat16* p) {
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
-                           __uint_as_float(r.y & 0xffff0000u));
-    }
-    static __device__ __forceinline__ float one(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
-};
-
-__device__ __forceinline__ float& comp(float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
-
-enum : int { kBefore = 0, kNow = 1, kAfter = 2 };
-
-// ---- per-thread asynchronous copies into the thread's own shared-memory ring slots -----------------------
-// (shared-memory operands are 32-bit shared-window addresses computed once per thread)
-__device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(unsigned smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(unsigned smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ float4 lds_f4(unsigned smem) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem));
-    return r;
-}
-__device__ __forceinline__ uint2 lds_u2(unsigned smem) {
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem));
-    return r;
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <typename LT>
-struct Slot;  // one thread's 4 logits of one class in the ring
-template <>
-struct Slot<float> {
-    static constexpr int kBytes = 16;
-    static constexpr bool kUnaligned = true;  // a quad at any 4-byte offset can be fetched as four 4-byte copies
-    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async16(s, g); }
-    static __device__ __forceinline__ void fetch_unaligned(unsigned s, const void* g) {
-        const char* b = static_cast<const char*>(g);
-        cp_async4(s, b), cp_async4(s + 4, b + 4), cp_async4(s + 8, b + 8), cp_async4(s + 12, b + 12);
-    }
-    static __device__ __forceinline__ float4 read(unsigned s) { return lds_f4(s); }
-};
-template <>
-struct Slot<__half> {
-    static constexpr int kBytes = 8;
-    static constexpr bool kUnaligned = false;
-    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
-    static __device__ __forceinline__ void fetch_unaligned(unsigned, const void*) {}
-    static __device__ __forceinline__ float4 read(unsigned s) {
-        const uint2 r = lds_u2(s);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-        return make_float4(a.x, a.y, b.x, b.y);
-    }
-};
-template <>
-struct Slot<__nv_bfloat16> {
-    static constexpr int kBytes = 8;
-    static constexpr bool kUnaligned = false;
-    static __device__ __forceinline__ void fetch(unsigned s, const void* g) { cp_async8(s, g); }
-    static __device__ __forceinline__ void fetch_unaligned(unsigned, const void*) {}
-    static __device__ __forceinline__ float4 read(unsigned s) {
-        const uint2 r = lds_u2(s);
-        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
-                           __uint_as_float(r.y & 0xffff0000u));
-    }
-};
-
-template <typename LT, int KC, int S>
-constexpr size_t acc_smem_bytes() {
-    return static_cast<size_t>(S) * kAccThreads * (16 + KC * Slot<LT>::kBytes);
-}
 
 // KC classes are held in registers per pass; S ring stages (windows) are in flight per thread.
 template <typename LT, int KC, int S, int MINB>
@@ -205,7 +72,8 @@ __global__ void __launch_bounds__(kAccThreads, MINB) accumulate_kernel(const __g
             const int id = dlo + c / (nw * nh);
             const long long n =
                 (static_cast<long long>(id - g.wlo[0]) * g.nwl[1] + (ih - g.wlo[1])) * g.nwl[2] + (iw - g.wlo[2]);
-            const int cls = n < n0 ? kBefore : (n >= n1 ? kAfter : kNow);
+            const long long ng = vol0 + n;
+            const int cls = (ng < p.own0 || ng >= p.own1) ? kForeign : (n < n0 ? kBefore : (n >= n1 ? kAfter : kNow));
             const int sd = g.starts[0][id], sh = g.starts[1][ih], sw = g.starts[2][iw];
             const int wofs = ((gd - sd) * rh - sh) * rw - sw;
             s_sh[tid] = sh;
@@ -527,10 +395,10 @@ static cudaError_t launch_for_k(int K, dim3 grid, cudaStream_t s, const AccParam
 
 using namespace mss;
 
-extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
-                              int32_t logits_dtype, int64_t first_window, int64_t n_windows, const float* importance_map,
-                              float* acc, int32_t fuse, uint8_t* labels, int32_t label_pitch_w, float tie_tol,
-                              unsigned long long* near_ties, void* stream) {
+static int accumulate_impl(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
+                           int32_t logits_dtype, int64_t first_window, int64_t n_windows, int64_t own_first,
+                           int64_t own_count, const float* importance_map, float* acc, int32_t fuse, uint8_t* labels,
+                           int32_t label_pitch_w, float tie_tol, unsigned long long* near_ties, void* stream) {
     AccParams p;
     int rc = make_geo(lay, &p.g);
     if (rc != MSS_OK) return rc;
@@ -553,11 +421,23 @@ extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_
     MSS_REQUIRE(static_cast<long long>(g.img[1]) * g.roi[2] + g.img[2] < (1LL << 31) &&
                     static_cast<long long>(g.roi[0]) * g.roi[1] * g.roi[2] < (1LL << 30),
                 MSS_E_UNSUPPORTED, "accumulate: roi / image too large for 32-bit window offsets");
+    if (own_count < 0) own_first = 0, own_count = total;  // the whole box
+    MSS_REQUIRE(own_first >= 0 && own_count > 0 && own_first + own_count <= total, MSS_E_ARG,
+                "accumulate: owned range [%lld, +%lld) outside [0, %lld)", static_cast<long long>(own_first),
+                static_cast<long long>(own_count), total);
+    MSS_REQUIRE(first_window >= own_first && first_window + n_windows <= own_first + own_count, MSS_E_ARG,
+                "accumulate: windows [%lld, +%lld) outside the owned range [%lld, +%lld)", static_cast<long long>(first_window),
+                static_cast<long long>(n_windows), static_cast<long long>(own_first), static_cast<long long>(own_count));
+    p.own0 = own_first;
+    p.own1 = own_first + own_count;
     const bool covers_all = first_window == 0 && n_windows == total;
-    if (fuse != MSS_FUSE_NONE)
+    if (fuse != MSS_FUSE_NONE) {
         for (int a = 0; a < 3; ++a)
             MSS_REQUIRE(g.wlo[a] == 0 && g.whi[a] == g.ns[a], MSS_E_ARG,
                         "accumulate: fused finishing needs a buffer that owns every window (axis %d)", a);
+        MSS_REQUIRE(own_first == 0 && own_count == total, MSS_E_ARG,
+                    "accumulate: fused finishing needs a buffer that owns every window (owned range is partial)");
+    }
     if (fuse == MSS_FUSE_LABELS) {
         MSS_REQUIRE(labels != nullptr && label_pitch_w >= g.ext[2], MSS_E_ARG, "accumulate: labels buffer / pitch invalid");
         MSS_REQUIRE(g.K <= 255, MSS_E_UNSUPPORTED, "accumulate: uint8 labels need K <= 255");
@@ -609,17 +489,25 @@ extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_
         p.box_lo[a] = lo[a];
         p.box_n[a] = hi[a] - lo[a];
     }
+    p.b_lo = b_lo;
     p.nq = (p.box_n[2] + 3) / 4;
+    cudaStream_t s = as_stream(stream);
+    // the cell-uniform kernel (accumulate_cells.cu) serves every geometry that fits its tables; the general kernel the rest
+    {
+        cudaError_t cerr = cudaSuccess;
+        if (launch_cells(lay, p, logits_dtype, s, &cerr) == 0) {
+            MSS_CUDA(cerr);
+            return MSS_OK;
+        }
+    }
     // tile: up to 32 quads (128 voxels) along W, split evenly; as many rows as fit 128 threads
     p.n_wtiles = (p.nq + 31) / 32;
     p.tq = (p.nq + p.n_wtiles - 1) / p.n_wtiles;
     p.th = kAccThreads / p.tq;
-    p.b_lo = b_lo;
     const int n_htiles = (p.box_n[1] + p.th - 1) / p.th;
     dim3 grid(static_cast<unsigned>(p.n_wtiles * n_htiles), static_cast<unsigned>(p.box_n[0]),
               static_cast<unsigned>(b_hi - b_lo + 1));
     MSS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MSS_E_UNSUPPORTED, "accumulate: box too large for one launch");
-    cudaStream_t s = as_stream(stream);
     cudaError_t e;
     if (logits_dtype == MSS_F32)
         e = launch_for_k<float>(g.K, grid, s, p);
@@ -629,4 +517,20 @@ extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_
         e = launch_for_k<__nv_bfloat16>(g.K, grid, s, p);
     MSS_CUDA(e);
     return MSS_OK;
+}
+
+extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
+                              int32_t logits_dtype, int64_t first_window, int64_t n_windows, const float* importance_map,
+                              float* acc, int32_t fuse, uint8_t* labels, int32_t label_pitch_w, float tie_tol,
+                              unsigned long long* near_ties, void* stream) {
+    return accumulate_impl(lay, batch_ptrs, n_batches, sw_batch, logits_dtype, first_window, n_windows, 0, -1, importance_map,
+                           acc, fuse, labels, label_pitch_w, tie_tol, near_ties, stream);
+}
+
+extern "C" int mss_accumulate_range(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches,
+                                    int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
+                                    int64_t own_first, int64_t own_count, const float* importance_map, float* acc,
+                                    void* stream) {
+    return accumulate_impl(lay, batch_ptrs, n_batches, sw_batch, logits_dtype, first_window, n_windows, own_first, own_count,
+                           importance_map, acc, MSS_FUSE_NONE, nullptr, 0, 0.f, nullptr, stream);
 }

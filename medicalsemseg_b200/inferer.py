@@ -138,8 +138,9 @@ def get_plan(spatial: Sequence[int], roi_size: Any, overlap: float, device: torc
 
 
 def _default_group_bytes(device: torch.device) -> int:
+    """Logits kept alive per accumulate launch: half of what is free, at most 64 GiB (180 GB of HBM3e per B200)."""
     free, _total = torch.cuda.mem_get_info(device)
-    return int(min(24 << 30, free // 2))
+    return int(min(64 << 30, free // 2))
 
 
 class Stitcher:
@@ -225,6 +226,14 @@ class Stitcher:
         self.group_batches = int(max(1, min(_lib.MAX_BATCH_PTRS, budget // max(per_batch, 1))))
         n_batches_total = -(-self.total // self.sw_batch)
         single_group = n_batches_total <= self.group_batches
+        if not single_group:
+            # several launches: cut between whole D layers of windows (windows are enumerated D-slowest), so the slab of
+            # unfinished fp32 sums a launch leaves for the next one is the 50 % overlap of two layers, not a full roi
+            nl = [h - l for l, h in zip(self.plan.win_lo, self.plan.win_hi)]
+            layer = nl[1] * nl[2]
+            k_layers = (self.group_batches * self.sw_batch) // max(layer, 1)
+            if k_layers >= 1:
+                self.group_batches = int(min(_lib.MAX_BATCH_PTRS, -(-(k_layers * layer) // self.sw_batch)))
         ext = self.plan.extent
         if self.fuse == _lib.FUSE_LABELS:
             self.labels = torch.empty((self.plan.n_volumes,) + tuple(ext), dtype=torch.uint8, device=self.device)

@@ -174,7 +174,8 @@ def test_fullsize_geometry_bit_identical_to_the_reference_run(name):
     # (2) many launches (accumulator read-modify-write between them): bit-identical to (1), hence to the reference
     st2 = mss.InferStats()
     out2 = mss.sliding_window_inference(vol, affine, c["roi"], c["sw_batch"], ArithmeticPredictor(k), overlap=c["overlap"],
-                                        mode=c["mode"], mss_stats=st2, mss_group_bytes=1 << 30)
+                                        mode=c["mode"], mss_stats=st2,
+                                        mss_group_bytes=min(1 << 30, 4 * k * 96 ** 3 * st.n_windows // 4))
     assert st2.n_accumulate_calls > st.n_accumulate_calls
     assert torch.equal(out, out2)
     del out2
@@ -185,7 +186,7 @@ def test_fullsize_geometry_bit_identical_to_the_reference_run(name):
     st3 = mss.InferStats()
     labels = mss.sliding_window_infer(vol, ArithmeticPredictor(k), c["roi"], c["overlap"], c["mode"], sw_batch_size=c["sw_batch"],
                                       affine=affine, stats=st3)[0]
-    assert not st3.accumulator_allocated
+    assert st3.accumulator_allocated == (st3.n_accumulate_calls > 1)  # one launch never materialises the fp32 volume
     # the reference's labels = plain first-max argmax of the (bit-identical) logits, except the handful of voxels where float32
     # softmax rounding merges a near-tie (stored by make_golden.py: index + the reference's label there)
     ref = out[0].argmax(dim=0).to(torch.uint8)
