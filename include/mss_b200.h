@@ -164,6 +164,19 @@ int mss_finalize_labels(const mss_layout_t* lay, const float* logits, const floa
                         uint8_t* labels, int32_t label_pitch_w, float* logits_out, float* probs_out,
                         float tie_tol, unsigned long long* near_ties, void* stream);
 
+/* Multi-GPU finalise that IS the exchange (no counterpart in the single-process reference; it is the `+=` of
+ * engine/utils.py:147 between ranks followed by :151 and engine/test.py:140-141).  `lay` describes the box this rank OWNS
+ * (origin / extent in the global frame, origin W a multiple of 4) over the GLOBAL window grid.  src_acc[i] is the raw-sum
+ * accumulator [Nb, K, extent_i, pitch_i] of rank i over its box src_origin[3i..] / src_extent[3i..] (W origin and pitch
+ * multiples of 4, zero where the rank accumulated nothing) - its own memory or a peer's mapped over NVLink (torch
+ * symmetric memory).  Every owned voxel adds the sources that hold it in ascending order, then either stores the first-max
+ * argmax into labels[Nb, extent, label_pitch_w] or (logits_out != NULL, [Nb, K, extent_d, extent_h, lay->pitch_w]) also
+ * the sums divided by the window-weight count of the global grid. */
+int mss_finalize_gather(const mss_layout_t* lay, int32_t n_src, const float* const* src_acc, const int32_t* src_origin,
+                        const int32_t* src_extent, const int32_t* src_pitch_w, const float* importance_map,
+                        uint8_t* labels, int32_t label_pitch_w, float* logits_out, float tie_tol,
+                        unsigned long long* near_ties, void* stream);
+
 /* Ensemble majority vote (majority_vote.py:23-37): votes[0] = 1, votes[c>=1] = #{m : map_m == c},
  * labels >= n_classes ignored, first-max argmax.  maps[i] are device pointers to n_voxels uint8. */
 int mss_majority_vote(const uint8_t* const* maps, int32_t n_maps, int32_t n_classes, int64_t n_voxels,

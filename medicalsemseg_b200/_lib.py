@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mss_accumulate_range": (C.c_int, [C.POINTER(Layout), C.POINTER(vp), c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, vp,
                                        vp, vp]),
     "mss_finalize_labels": (C.c_int, [C.POINTER(Layout), vp, vp, c_i32, I3, I3, vp, c_i32, vp, vp, c_f32, vp, vp]),
+    "mss_finalize_gather": (C.c_int, [C.POINTER(Layout), c_i32, C.POINTER(vp), vp, vp, vp, vp, vp, c_i32, vp, c_f32, vp, vp]),
     "mss_majority_vote": (C.c_int, [C.POINTER(vp), c_i32, c_i32, c_i64, vp, vp]),
     "mss_dice_counts": (C.c_int, [vp, vp, c_i32, c_i64, c_i32, vp, vp]),
     "mss_dice_counts_batched": (C.c_int, [vp, vp, c_i32, c_i64, c_i64, c_i32, vp, vp]),

@@ -50,8 +50,9 @@ struct Geo {
     const int* cover[3];  // per global coordinate: lo | (hi << 16), hi exclusive
 };
 
-// Validates `lay` and fills `g`; host side only.
-int make_geo(const mss_layout_t* lay, Geo* g);
+// Validates `lay` and fills `g`; host side only.  windows_inside: the owned windows must lie inside the buffer box (not
+// the case for the box a rank merely OWNS in mss_finalize_gather).
+int make_geo(const mss_layout_t* lay, Geo* g, bool windows_inside = true);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -328,3 +328,168 @@ extern "C" int mss_finalize_labels(const mss_layout_t* lay, const float* logits,
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }
+
+// ---- multi-GPU: the finalise step that IS the exchange ---------------------------------------------------------------
+// One volume, its window list cut into one contiguous range per rank (flat partition): every rank holds raw weighted sums
+// of ITS windows over the bounding box of their footprints (zero where none of them reaches).  The rank that owns a box of
+// the volume finishes it by reading every contributing accumulator - its own and its peers', mapped over NVLink - adding
+// them in ascending rank order (= ascending window order between ranks), and taking the argmax: no halo buffers, no
+// send / recv, no separate add pass.
+namespace mss {
+
+constexpr int kMaxGatherSrc = 16;
+
+struct GatherParams {
+    Geo g;  // org / ext = the owned box (global frame), pitch = pitch of logits_out
+    const float* src[kMaxGatherSrc];
+    int so[kMaxGatherSrc][3];  // source box origin (global), extent, W pitch
+    int se[kMaxGatherSrc][3];
+    int sp[kMaxGatherSrc];
+    int n_src;
+    const float* imp;
+    uint8_t* labels;
+    int label_pitch;
+    float* logits_out;
+    float tie_tol;
+    unsigned long long* near_ties;
+    int nq;
+};
+
+__global__ void __launch_bounds__(kFinThreads) finalize_gather_kernel(const __grid_constant__ GatherParams p) {
+    const Geo& g = p.g;
+    const int t = blockIdx.x * kFinThreads + threadIdx.x;
+    const bool in_box = t < p.nq * g.ext[1];
+    const int row = in_box ? t / p.nq : 0;
+    const int ld = blockIdx.y, lh = row, lw = (in_box ? t - row * p.nq : 0) * 4;
+    const int b = blockIdx.z;
+    const int gd = ld + g.org[0], gh = lh + g.org[1], gw = lw + g.org[2];
+    bool valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) valid[e] = in_box && lw + e < g.ext[2];
+    unsigned ties = 0;
+    if (valid[0]) {
+        const int K = g.K;
+        // the accumulators that hold this quad (a box test; what a rank did not touch inside its box is zero)
+        const float* ptr[kMaxGatherSrc];
+        long long cs[kMaxGatherSrc];
+        int n_hit = 0;
+#pragma unroll
+        for (int q = 0; q < kMaxGatherSrc; ++q) {
+            if (q < p.n_src) {
+                const int d = gd - p.so[q][0], h = gh - p.so[q][1], w = gw - p.so[q][2];
+                if (static_cast<unsigned>(d) < static_cast<unsigned>(p.se[q][0]) &&
+                    static_cast<unsigned>(h) < static_cast<unsigned>(p.se[q][1]) && w >= 0 && w < p.sp[q]) {
+                    const long long plane = static_cast<long long>(p.se[q][1]) * p.sp[q];
+                    cs[n_hit] = static_cast<long long>(p.se[q][0]) * plane;
+                    ptr[n_hit] = p.src[q] + static_cast<long long>(b) * K * cs[n_hit] + static_cast<long long>(d) * plane +
+                                 static_cast<long long>(h) * p.sp[q] + w;
+                    ++n_hit;
+                }
+            }
+        }
+        float cnt[4] = {1.f, 1.f, 1.f, 1.f};
+        if (p.logits_out != nullptr) weight_count(g, p.imp, gd, gh, gw, valid, cnt);
+        ArgmaxState am[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) am[e].reset();
+        const long long oplane = static_cast<long long>(g.ext[1]) * g.pitch;
+        const long long ocs = static_cast<long long>(g.ext[0]) * oplane;
+        for (int k = 0; k < K; ++k) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < n_hit; ++q) {
+                const float4 s = ld_stream_f4(ptr[q] + k * cs[q]);
+                v.x = __fadd_rn(v.x, s.x);
+                v.y = __fadd_rn(v.y, s.y);
+                v.z = __fadd_rn(v.z, s.z);
+                v.w = __fadd_rn(v.w, s.w);
+            }
+            if (p.logits_out != nullptr) {
+                v.x = __fdiv_rn(v.x, cnt[0]);  // engine/utils.py:151
+                v.y = __fdiv_rn(v.y, cnt[1]);
+                v.z = __fdiv_rn(v.z, cnt[2]);
+                v.w = __fdiv_rn(v.w, cnt[3]);
+                float* dst = p.logits_out + (static_cast<long long>(b) * K + k) * ocs + static_cast<long long>(ld) * oplane +
+                             static_cast<long long>(lh) * g.pitch + lw;
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+            am[0].push(v.x, k);
+            am[1].push(v.y, k);
+            am[2].push(v.z, k);
+            am[3].push(v.w, k);
+        }
+        if (p.labels != nullptr) {
+            uint8_t* lab = p.labels + (static_cast<long long>(b) * g.ext[0] + ld) * g.ext[1] * p.label_pitch +
+                           static_cast<long long>(lh) * p.label_pitch + lw;
+            unsigned packed = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (valid[e]) {
+                    packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
+                    ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
+                }
+            if (valid[3] && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0)) {
+                *reinterpret_cast<unsigned*>(lab) = packed;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (valid[e]) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+            }
+        }
+    }
+    if (p.near_ties != nullptr) {
+        const unsigned warp_ties = __reduce_add_sync(0xffffffffu, ties);
+        if (warp_ties != 0u && (threadIdx.x & 31) == 0) atomicAdd(p.near_ties, static_cast<unsigned long long>(warp_ties));
+    }
+}
+
+}  // namespace mss
+
+extern "C" int mss_finalize_gather(const mss_layout_t* lay, int32_t n_src, const float* const* src_acc,
+                                   const int32_t* src_origin, const int32_t* src_extent, const int32_t* src_pitch_w,
+                                   const float* importance_map, uint8_t* labels, int32_t label_pitch_w, float* logits_out,
+                                   float tie_tol, unsigned long long* near_ties, void* stream) {
+    GatherParams p;
+    int rc = make_geo(lay, &p.g, false);
+    if (rc != MSS_OK) return rc;
+    const Geo& g = p.g;
+    MSS_REQUIRE(src_acc && src_origin && src_extent && src_pitch_w, MSS_E_ARG, "finalize_gather: null argument");
+    MSS_REQUIRE(n_src >= 1 && n_src <= kMaxGatherSrc, MSS_E_ARG, "finalize_gather: n_src %d outside [1, %d]", n_src,
+                kMaxGatherSrc);
+    MSS_REQUIRE(labels != nullptr || logits_out != nullptr, MSS_E_ARG, "finalize_gather: nothing to write");
+    MSS_REQUIRE(logits_out == nullptr || importance_map != nullptr, MSS_E_ARG,
+                "finalize_gather: normalised logits need the importance map");
+    MSS_REQUIRE(labels == nullptr || (g.K <= 255 && label_pitch_w >= g.ext[2]), MSS_E_ARG,
+                "finalize_gather: uint8 labels need K <= 255 and label_pitch_w >= extent W");
+    MSS_REQUIRE(g.org[2] % 4 == 0, MSS_E_ALIGN, "finalize_gather: the owned box must start on a multiple of 4 along W");
+    MSS_REQUIRE(logits_out == nullptr || (g.pitch % 4 == 0 && reinterpret_cast<uintptr_t>(logits_out) % 16 == 0), MSS_E_ALIGN,
+                "finalize_gather: logits_out needs a pitch multiple of 4 and a 16-byte aligned base");
+    for (int q = 0; q < n_src; ++q) {
+        MSS_REQUIRE(src_acc[q] != nullptr && reinterpret_cast<uintptr_t>(src_acc[q]) % 16 == 0, MSS_E_ALIGN,
+                    "finalize_gather: source %d is null or not 16-byte aligned", q);
+        MSS_REQUIRE(src_pitch_w[q] % 4 == 0 && src_origin[3 * q + 2] % 4 == 0 && src_pitch_w[q] >= src_extent[3 * q + 2],
+                    MSS_E_ALIGN, "finalize_gather: source %d needs W origin and pitch multiples of 4", q);
+        p.src[q] = src_acc[q];
+        p.sp[q] = src_pitch_w[q];
+        for (int a = 0; a < 3; ++a) {
+            MSS_REQUIRE(src_extent[3 * q + a] > 0 && src_origin[3 * q + a] >= 0, MSS_E_ARG,
+                        "finalize_gather: source %d has an empty box", q);
+            p.so[q][a] = src_origin[3 * q + a];
+            p.se[q][a] = src_extent[3 * q + a];
+        }
+    }
+    p.n_src = n_src;
+    p.imp = importance_map;
+    p.labels = labels;
+    p.label_pitch = label_pitch_w;
+    p.logits_out = logits_out;
+    p.tie_tol = tie_tol;
+    p.near_ties = near_ties;
+    p.nq = (g.ext[2] + 3) / 4;
+    const long long per_plane = static_cast<long long>(p.nq) * g.ext[1];
+    dim3 grid(static_cast<unsigned>((per_plane + kFinThreads - 1) / kFinThreads), static_cast<unsigned>(g.ext[0]),
+              static_cast<unsigned>(g.nb));
+    MSS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MSS_E_UNSUPPORTED, "finalize_gather: box too large for one launch");
+    finalize_gather_kernel<<<grid, kFinThreads, 0, as_stream(stream)>>>(p);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}

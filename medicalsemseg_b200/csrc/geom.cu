@@ -24,7 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     return static_cast<int>(e);
 }
 
-int make_geo(const mss_layout_t* lay, Geo* g) {
+int make_geo(const mss_layout_t* lay, Geo* g, bool windows_inside) {
     MSS_REQUIRE(lay != nullptr, MSS_E_ARG, "layout is null");
     MSS_REQUIRE(lay->table_host != nullptr && lay->table_dev != nullptr, MSS_E_ARG, "layout tables are null");
     const int32_t* t = lay->table_host;
@@ -44,8 +44,8 @@ int make_geo(const mss_layout_t* lay, Geo* g) {
                     lay->extent[a], lay->image[a]);
         // every owned window must lie inside the buffer
         const int32_t* st = t + t[kHdrOffStarts + a];
-        MSS_REQUIRE(st[lay->win_lo[a]] >= lay->origin[a] &&
-                        st[lay->win_hi[a] - 1] + lay->roi[a] <= lay->origin[a] + lay->extent[a],
+        MSS_REQUIRE(!windows_inside || (st[lay->win_lo[a]] >= lay->origin[a] &&
+                                        st[lay->win_hi[a] - 1] + lay->roi[a] <= lay->origin[a] + lay->extent[a]),
                     MSS_E_ARG, "axis %d: owned windows reach outside the buffer box", a);
         g->img[a] = lay->image[a];
         g->roi[a] = lay->roi[a];

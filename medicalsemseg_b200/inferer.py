@@ -154,8 +154,12 @@ class Stitcher:
     def __init__(self, plan: StitchPlan, imp: torch.Tensor, *, fuse: int, sw_batch: int, tie_tol: float = 1e-5,
                  group_bytes: Optional[int] = None, stats: Optional[InferStats] = None, time_kernels: bool = False,
                  use_tma: bool = True, extract_bytes: Optional[int] = None,
-                 acc_alloc: Optional[Callable[[Tuple[int, ...]], torch.Tensor]] = None):
+                 acc_alloc: Optional[Callable[[Tuple[int, ...]], torch.Tensor]] = None,
+                 own_range: Optional[Tuple[int, int]] = None):
         self.lib = _lib.load()
+        # multi-GPU flat partition: only windows [first, first + count) of the plan's box are this rank's; the raw sums go
+        # into a ZEROED accumulator through mss_accumulate_range (the other windows of the box do not exist here)
+        self.own_range = None if own_range is None else (int(own_range[0]), int(own_range[1]))
         self.acc_alloc = acc_alloc  # where the fp32 accumulator lives (peer-mapped symmetric memory for multi-GPU halos)
         self.extract_bytes = int(extract_bytes) if extract_bytes is not None else (1 << 30)
         self.plan, self.imp, self.fuse, self.sw_batch = plan, imp, fuse, int(sw_batch)
@@ -166,8 +170,13 @@ class Stitcher:
         self.use_tma = use_tma
         self.device = plan.device
         self.total = plan.n_local * plan.n_volumes
+        self.first = 0
+        if self.own_range is not None:
+            if fuse != _lib.FUSE_NONE:
+                raise ValueError("a partial window range accumulates raw sums only (fuse must be FUSE_NONE)")
+            self.first, self.total = self.own_range
         self.pending: List[torch.Tensor] = []
-        self.pending_first = 0
+        self.pending_first = self.first
         self.pending_windows = 0
         self.acc: Optional[torch.Tensor] = None
         self.labels: Optional[torch.Tensor] = None
@@ -209,10 +218,10 @@ class Stitcher:
         ahead = max(ahead, self.sw_batch)
         for g0 in range(0, self.total, ahead):
             gn = min(ahead, self.total - g0)
-            patches, centers = self.extract(volume, g0, gn, cval, vol_origin)
+            patches, centers = self.extract(volume, self.first + g0, gn, cval, vol_origin)
             for off in range(0, gn, self.sw_batch):
                 n = min(self.sw_batch, gn - off)
-                yield g0 + off, n, patches[off:off + n], centers[off:off + n]
+                yield self.first + g0 + off, n, patches[off:off + n], centers[off:off + n]
 
     # -- accumulation ---------------------------------------------------------------------------
     def _first_batch(self, logits: torch.Tensor) -> None:
@@ -242,6 +251,8 @@ class Stitcher:
             shape = (self.plan.n_volumes, self.K, ext[0], ext[1], self.plan.pitch_w)
             self.acc = (self.acc_alloc(shape) if self.acc_alloc is not None
                         else torch.empty(shape, dtype=torch.float32, device=self.device))
+            if self.own_range is not None:
+                self.acc.zero_()  # voxels of the box none of this rank's windows reaches must read as zero
             if self.stats is not None:
                 self.stats.accumulator_allocated = True
 
@@ -262,7 +273,7 @@ class Stitcher:
             logits = logits.clone()  # a predictor that reuses its output buffer (e.g. a captured CUDA graph)
         self.pending.append(logits)
         self.pending_windows += n
-        if len(self.pending) >= self.group_batches or self.pending_first + self.pending_windows >= self.total:
+        if len(self.pending) >= self.group_batches or self.pending_first + self.pending_windows >= self.first + self.total:
             self.flush()
 
     def flush(self) -> None:
@@ -272,11 +283,17 @@ class Stitcher:
         ptrs = (C.c_void_p * len(self.pending))(*[t.data_ptr() for t in self.pending])
         stream = torch.cuda.current_stream().cuda_stream
         with self.timer("accumulate"):
-            rc = self.lib.mss_accumulate(
-                C.byref(self.lay), ptrs, len(self.pending), self.sw_batch, _DTYPES[self.logits_dtype], self.pending_first,
-                self.pending_windows, self.imp.data_ptr(), None if self.acc is None else self.acc.data_ptr(), self.fuse,
-                None if self.labels is None else self.labels.data_ptr(), self.plan.extent[2], self.tie_tol,
-                self.near.data_ptr(), stream)
+            if self.own_range is not None:
+                rc = self.lib.mss_accumulate_range(
+                    C.byref(self.lay), ptrs, len(self.pending), self.sw_batch, _DTYPES[self.logits_dtype], self.pending_first,
+                    self.pending_windows, self.own_range[0], self.own_range[1], self.imp.data_ptr(), self.acc.data_ptr(),
+                    stream)
+            else:
+                rc = self.lib.mss_accumulate(
+                    C.byref(self.lay), ptrs, len(self.pending), self.sw_batch, _DTYPES[self.logits_dtype], self.pending_first,
+                    self.pending_windows, self.imp.data_ptr(), None if self.acc is None else self.acc.data_ptr(), self.fuse,
+                    None if self.labels is None else self.labels.data_ptr(), self.plan.extent[2], self.tie_tol,
+                    self.near.data_ptr(), stream)
         _lib.check(rc, "mss_accumulate")
         if self.stats is not None:
             self.stats.gpu_launches += 1
