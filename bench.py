@@ -12,9 +12,18 @@ every patch batch, all logits stitched, labels produced.  Workloads (BASELINE.js
     brats      cfg4  1x4x240x240x155, K=3, 5-model ensemble sharded over the ranks -> majority vote
     cfg1             1x1x128^3, UNet, overlap .25, N=8
 
-With N > 1 ranks the default shards VOLUMES (cfg5: one btcv volume per rank and step, Dice counts all-reduced;
-no data-path collective, "scaling": "weak"); --workload wholebody partitions ONE volume into slabs with a halo
-exchange ("strong").  Prints ONE JSON line on rank 0.
+With N > 1 ranks the headline shards VOLUMES (cfg5: one btcv volume per rank and step, Dice counts all-reduced;
+no data-path collective, "scaling": "weak").  The same line carries the other measured legs (benchmarks/legs.py):
+
+    strong_scaling  ONE wholebody volume cut over the N ranks (flat partition, peer-memory finalise): the north-star curve
+    ensemble        the 5-model brats ensemble sharded over the ranks + majority vote
+    parity          (N > 1) tests/multigpu_parity.py's checks against the CPU oracle, run once before timing
+    kernels         (N = 1) every non-backbone kernel at cfg2 and cfg4 sizes against the HBM roofline
+    stitch_only     (N = 1) the path with a cheap predictor: this repo vs the reference's ATen op sequence on the same GPU
+    cpu_baseline    (N = 1) the reference's CPU path (oracle port) on the host cores: bounded sample + measured legs
+
+--workload wholebody / brats print that leg as the headline instead; --no-legs prints the headline alone.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -114,16 +123,31 @@ def physical_gpu_index(local: int) -> int:
 # reference arm: the reference's CPU path (oracle port of engine/utils.py + engine/test.py:140-141), bounded sample
 # ---------------------------------------------------------------------------------------------------------------
 
+def config_dict(args, wl) -> dict:
+    """The workload description both arms print (identical dicts: same metric on the same configuration)."""
+    from medicalsemseg_b200.grid import make_grid
+
+    nb, cin, d, h, w = wl["shape"]
+    n_win = make_grid((d, h, w), ROI, wl["overlap"]).n_windows * nb
+    return {"workload": args.workload, "baseline_config": wl["cfg"], "shape": list(wl["shape"]), "roi": ROI,
+            "overlap": wl["overlap"], "classes": wl["k"], "blend": "gaussian", "windows": n_win, "sw_batch": args.sw_batch,
+            "backbone": wl["backbone"] + " (benchmarks/backbones.py, random init, seed 13, fp32 eager torch)",
+            "l2_policy": f"inputs larger than L2: {4 * n_win * wl['k'] * ROI ** 3 / 1e9:.1f} GB of logits per step stream "
+                         "through the 126 MB L2"}
+
+
 def cpu_reference_sample(wl: dict, repeats: int, warmup: int, sw_batch: int = 4):
     """Times the oracle on a strip of the workload holding `n_s` windows with the same backbone on the host cores and
-    extrapolates to the full volume: T_full = T_stitch+backbone * (N / n_s) + T_labels * (V / V_s)."""
+    extrapolates to the full volume: T_full = T_stitch+backbone * (N / n_s) + T_labels * (V / V_s).  cfg1 (8 windows)
+    is timed whole."""
     from benchmarks.backbones import build_backbone
     from oracle import sliding_window as osw
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nb, cin, d, h, w = wl["shape"]
-    sd, sh = min(d, ROI), min(h, ROI)
+    whole = d * h * w <= 128 ** 3
+    sd, sh = (d, h) if whole else (min(d, ROI), min(h, ROI))
     sample_shape = (1, cin, sd, sh, w)  # one row of windows along W
     model = build_backbone(wl["backbone"], cin, wl["k"])
     rs = np.random.RandomState(0)
@@ -145,23 +169,64 @@ def cpu_reference_sample(wl: dict, repeats: int, warmup: int, sw_batch: int = 4)
             if it >= warmup:
                 times.append((t1 - t0) * (n_full / n_s) + (t2 - t1) * (v_full / v_s))
     t_full = float(np.mean(times))
-    sample = (f"oracle (port of engine/utils.py + engine/test.py:140-141) with the same {wl['backbone']} backbone on a "
-              f"{sd}x{sh}x{w} strip = {n_s} of {n_full} windows, sw_batch {sw_batch}, torch {cores} threads; per-window time scaled by "
-              f"{n_full}/{n_s}, label time by voxels (extrapolated)")
+    how = "the whole volume, measured" if whole else (
+        f"a {sd}x{sh}x{w} strip = {n_s} of {n_full} windows; per-window time scaled by {n_full}/{n_s}, label time by voxels "
+        "(EXTRAPOLATED: the full volume needs ~6 min per step on the host)")
+    sample = (f"oracle = port of engine/utils.py + engine/test.py:140-141 (the reference itself needs MONAI and is not on the GPU "
+              f"box) with the same {wl['backbone']} backbone on {how}; sw_batch {sw_batch}, torch {cores} threads, "
+              f"{repeats} timed repeats after {warmup} warm-up")
     return v_full / t_full, t_full, cores, sample
+
+
+def cpu_measured_legs(sw_batch: int) -> dict:
+    """The CPU numbers that are measured, not extrapolated: cfg1 end to end with its UNet, and the
+    non-backbone path of cfg2 over ALL 400 windows with the cheap predictor."""
+    from benchmarks.backbones import build_backbone
+    from benchmarks.legs import CheapPredictor
+    from oracle import sliding_window as osw
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {}
+    wl = WORKLOADS["cfg1"]
+    model = build_backbone(wl["backbone"], 1, wl["k"])
+    vol = torch.from_numpy(np.random.RandomState(0).standard_normal(wl["shape"]).astype(np.float32))
+    with torch.no_grad():
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            o = osw.sliding_window_inference(vol, torch.ones(1, 3), ROI, 4, model, overlap=wl["overlap"], mode="gaussian",
+                                             tuple_input=False)
+            osw.labels_from_logits(o)
+            ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts[1:]))
+    out["cfg1_end_to_end"] = {"seconds": t, "voxels_per_s": 128 ** 3 / t, "windows": 8, "backbone": "unet", "cores": cores,
+                              "what": "BASELINE.json configs[0] whole: oracle sliding window + UNet + softmax/argmax, 2 repeats after 1 warm-up"}
+    wl = WORKLOADS["btcv"]
+    vol = torch.from_numpy(np.random.RandomState(0).standard_normal(wl["shape"]).astype(np.float32))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        o = osw.sliding_window_inference(vol, None, ROI, sw_batch, CheapPredictor(wl["k"]), overlap=wl["overlap"], mode="gaussian",
+                                         tuple_input=False)
+        t1 = time.perf_counter()
+        osw.labels_from_logits(o)
+        t2 = time.perf_counter()
+    out["cfg2_stitch_only_all_windows"] = {
+        "seconds": t2 - t0, "stitch_seconds": t1 - t0, "labels_seconds": t2 - t1, "voxels_per_s": 512 * 512 * 200 / (t2 - t0),
+        "windows": 400, "cores": cores,
+        "what": "non-backbone path of configs[1] over ALL 400 windows with the cheap predictor of benchmarks/legs.py, 1 run"}
+    return out
 
 
 def run_reference(args, wl) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, t_full, cores, sample = cpu_reference_sample(wl, args.steps, args.warmup, args.sw_batch)
+    value, t_full, cores, sample = cpu_reference_sample(wl, max(args.steps, 1), min(args.warmup, 1), args.sw_batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "shape": list(wl["shape"]), "roi": ROI,
-                                                        "overlap": wl["overlap"], "classes": wl["k"], "blend": "gaussian",
-                                                        "sw_batch": args.sw_batch},
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl),
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -183,16 +248,17 @@ def main() -> None:
     ap.add_argument("--sw-batch", type=int, default=8,
                     help="windows per backbone call (engine/utils.py sw_batch_size); 8 is 19%% faster than 4 on B200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="headline only (no strong-scaling / ensemble / kernels / stitch-only legs)")
     ap.add_argument("--group-gib", type=float, default=None, help="logits held per accumulate launch (default: auto)")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"], help="wholebody, N > 1: how halos travel")
-    ap.add_argument("--block-dims", default=None, help="wholebody, N > 1: ranks per axis as DxHxW (default: best balance)")
+    ap.add_argument("--partition", default="flat", choices=["flat", "block"], help="wholebody, N > 1: how the volume is cut")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":
         run_reference(args, wl)
         return
 
     import medicalsemseg_b200 as mss
+    from benchmarks import legs
     from benchmarks.backbones import build_backbone
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,14 +270,40 @@ def main() -> None:
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = peaks()
 
-    if args.workload == "wholebody" and world > 1:
-        from benchmarks.slab_bench import run_wholebody
-        run_wholebody(args, wl, rank, world, dev, dist)
-        return
-    if args.workload == "brats":
-        from benchmarks.ensemble_bench import run_ensemble
-        run_ensemble(args, wl, rank, world, dev, dist)
+    def finish(line=None):
+        if rank == 0 and line is not None:
+            print(json.dumps(line))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+
+    # ---- parity of the multi-GPU paths against the CPU oracle, once, before anything is timed --------------------------
+    parity = None
+    if world > 1 and not args.no_legs:
+        from tests import multigpu_parity
+        res = multigpu_parity.run_checks(rank, world, dev)
+        if rank == 0:
+            parity = multigpu_parity.summary(res)
+
+    if args.workload in ("wholebody", "brats"):  # that leg as the headline
+        sampler = ClockSampler(physical_gpu_index(local))
+        sampler.start()
+        if args.workload == "wholebody":
+            leg = legs.wholebody_leg(wl, rank, world, dev, dist, steps=args.steps, warmup=args.warmup, sw_batch=args.sw_batch,
+                                     partition=args.partition)
+        else:
+            leg = legs.ensemble_leg(wl, rank, world, dev, dist, steps=args.steps, warmup=args.warmup, sw_batch=args.sw_batch)
+        clocks = sampler.result()
+        line = None
+        if rank == 0:
+            line = {"metric": METRIC, "value": leg["voxels_per_s"], "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl), "clocks": clocks,
+                    "leg": leg, "parity": parity,
+                    "e2e": None, "gpu_launches": None, "note": "leg-only run: the contract line is the default workload's"}
+        finish(line)
         return
 
     nb, cin, d, h, w = wl["shape"]
@@ -276,37 +368,33 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
 
+    line = None
     if rank == 0:
-        peak, peak_src = peaks()
         kms = [s.kernel_ms() for s in stats]
         acc_launch_ms = [x for s in stats for x in s.kernel_launch_ms("accumulate")]
         n_win = stats[0].n_windows
         r = ROI**3
         n_acc = max(stats[0].n_accumulate_calls, 1)
         # algorithmic bytes of the accumulate kernel as built: every logit read once (4 N K R), plus the
-        # uint8 label of every voxel written once; when the windows need several launches (cfg3 on one GPU) each launch
-        # boundary leaves a roi-thick slab of unfinished voxels (windows are enumerated D-slowest) whose fp32 sums are
-        # written by one launch and read back by the next: 8 K roi H W bytes per boundary.
-        acc_bytes = 4 * n_win * k * r + v + (n_acc - 1) * 8 * k * ROI * h * w * nb
+        # uint8 label of every voxel written once; when the windows need several launches each launch boundary leaves a
+        # slab of unfinished voxels (windows are enumerated D-slowest; groups end on layer boundaries, so the slab is the
+        # half-roi overlap of two layers) whose fp32 sums are written by one launch and read back by the next
+        acc_bytes = 4 * n_win * k * r + v + (n_acc - 1) * 8 * k * (ROI // 2) * h * w * nb
         acc_ms_step = float(np.mean([m.get("accumulate", 0.0) for m in kms]))
         achieved = acc_bytes / (acc_ms_step * 1e-3) / 1e9 if acc_ms_step > 0 else None
+        cfg = config_dict(args, wl)
         line = {
             "metric": METRIC, "value": v * world * args.steps / (ms_total * 1e-3), "unit": "voxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "baseline_config": wl["cfg"], "shape": list(wl["shape"]), "roi": ROI,
-                "overlap": wl["overlap"], "classes": k, "blend": "gaussian", "windows": n_win, "sw_batch": args.sw_batch,
-                "backbone": wl["backbone"] + " (random init, seed 13, fp32 eager torch)", "volumes_per_step": world,
-                "l2_policy": f"inputs larger than L2: {4 * n_win * k * r / 1e9:.1f} GB of logits per step stream through the 126 MB L2",
-                "sharding": "one volume per rank, Dice counts all-reduced (cfg5 style)" if world > 1 else "single GPU",
-            },
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "sharding": {"volumes_per_step": world,
+                         "how": "one volume per rank, Dice counts all-reduced (cfg5 style)" if world > 1 else "single GPU"},
             "e2e": {"value": v * world * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": host_vol.numel() * 4, "d2h_bytes_per_step": host_labels.numel()},
             "gpu_launches": int(sum(s.gpu_launches for s in stats)),
             "clocks": clocks,
             "roofline": {
-                "kernel": "accumulate_kernel<float> (fused normalise+argmax)", "bound": "hbm", "achieved": achieved,
+                "kernel": "accumulate_cells_kernel<float, 7, 3> (fused normalise+argmax)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": ncu_traffic(f"accumulate_fused_labels_{args.workload}") if n_acc == 1 else None,
                 "algorithmic_bytes_per_launch": acc_bytes / n_acc, "launches_per_step": n_acc,
@@ -319,16 +407,39 @@ def main() -> None:
         }
         ext_ms = line["breakdown_ms_per_step"]["extract"]
         if ext_ms > 0:
-            line["roofline_extract"] = {"achieved": 8 * n_win * cin * r / (ext_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                        "note": "extract-ahead launches of up to 1 GiB of windows (re-reads of overlapping windows hit L2, "
-                                                "so algorithmic bytes / time can exceed the DRAM copy peak)"}
-        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 number
-            val, t_full, cores, sample = cpu_reference_sample(wl, repeats=1, warmup=0, sw_batch=args.sw_batch)
-            line["cpu_baseline"] = {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+            comp = 4 * v * cin + 4 * n_win * cin * r
+            line["roofline_extract"] = {"achieved": comp / (ext_ms * 1e-3) / 1e9, "frac": comp / (ext_ms * 1e-3) / 1e9 / peak,
+                                        "unit": "GB/s", "bytes": comp,
+                                        "note": "compulsory bytes: volume read once (4 V Cin) + patches written once (4 N Cin R); "
+                                                "re-reads of overlapping windows hit L2"}
+    del model, dev_vol, label_gt
+    torch.cuda.empty_cache()
+
+    # ---- the other measured legs ----------------------------------------------------------------------------------------
+    if not args.no_legs:
+        wb = legs.wholebody_leg(dict(WORKLOADS["wholebody"], name="wholebody"), rank, world, dev, dist, steps=2, warmup=1,
+                                sw_batch=args.sw_batch, partition=args.partition)
+        torch.cuda.empty_cache()
+        ens = legs.ensemble_leg(dict(WORKLOADS["brats"], name="brats"), rank, world, dev, dist, steps=2, warmup=1,
+                                sw_batch=args.sw_batch)
+        torch.cuda.empty_cache()
+        if rank == 0:
+            line["strong_scaling"] = wb
+            line["ensemble"] = ens
+            line["parity"] = parity
+            if world == 1:
+                line["kernels"] = legs.kernels_table(dev, peak)
+                line["stitch_only"] = legs.stitch_only(wl, dev, sw_batch=args.sw_batch)
+    if rank == 0 and not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 number
+        val, t_full, cores, sample = cpu_reference_sample(wl, repeats=3, warmup=1, sw_batch=args.sw_batch)
+        line["cpu_baseline"] = {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
+        if not args.no_legs:
+            line["cpu_baseline"]["measured"] = cpu_measured_legs(args.sw_batch)
+            if "stitch_only" in line:
+                cpu = line["cpu_baseline"]["measured"]["cfg2_stitch_only_all_windows"]
+                line["stitch_only"]["cpu"] = cpu
+                line["stitch_only"]["speedup_vs_cpu"] = cpu["seconds"] * 1e3 / line["stitch_only"]["ours"]["ms_per_volume"]
+    finish(line)
 
 
 if __name__ == "__main__":

@@ -20,17 +20,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import medicalsemseg_b200 as mss  # noqa: E402
-from medicalsemseg_b200 import block, slab  # noqa: E402
+from medicalsemseg_b200 import block, flat, slab  # noqa: E402
 from oracle import dice as odice  # noqa: E402
 from oracle import sliding_window as osw  # noqa: E402
 from oracle.predictors import ArithmeticPredictor  # noqa: E402
 
 
-def main() -> None:
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def run_checks(rank: int, world: int, dev: torch.device) -> dict:
+    """All ranks call this with torch.distributed (NCCL) initialised; rank 0 gets the result dict (others {})."""
     results = {}
     cases = [
         dict(shape=(1, 1, 40, 36, 40 * world + 24), roi=(16, 16, 16), overlap=0.5, k=5),       # long axis W
@@ -56,6 +53,13 @@ def main() -> None:
                                                               sw_batch_size=3, dims=c.get("dims"), halo="p2p")
         except Exception as e:  # noqa: BLE001 - symmetric memory unavailable on this box: reported, NCCL path stands
             plabels, p2p_err = None, f"{type(e).__name__}: {e}"[:200]
+        # the flat partition: contiguous window ranges, the finalise reads the peers' accumulators over NVLink
+        flat_err = None
+        try:
+            flabels, _, fpart = flat.sliding_window_infer_flat(vol, pred, c["roi"], c["overlap"], "gaussian", gather=True,
+                                                               sw_batch_size=3)
+        except Exception as e:  # noqa: BLE001
+            flabels, fpart, flat_err = None, None, f"{type(e).__name__}: {e}"[:200]
         torch.cuda.synchronize()
         if rank == 0:
             ref = osw.sliding_window_inference(vol, None, c["roi"], 3, pred, overlap=c["overlap"], mode="gaussian",
@@ -74,7 +78,10 @@ def main() -> None:
                 "block_dims": list(bpart.dims), "block_windows_per_rank": [bpart.n_windows(r) for r in range(world)],
                 "block_mismatch_vs_oracle": int(((blabels.cpu().numpy() != want) & ~near).sum()),
                 "p2p_used": bool(plabels is not None and block.can_exchange_p2p(bpart)), "p2p_error": p2p_err,
-                "p2p_mismatch_vs_oracle": None if plabels is None else int(((plabels.cpu().numpy() != want) & ~near).sum())})
+                "p2p_mismatch_vs_oracle": None if plabels is None else int(((plabels.cpu().numpy() != want) & ~near).sum()),
+                "flat_error": flat_err,
+                "flat_windows_per_rank": None if fpart is None else [fpart.n_windows(r) for r in range(world)],
+                "flat_mismatch_vs_oracle": None if flabels is None else int(((flabels.cpu().numpy() != want) & ~near).sum())})
             results[f"case{ci}"] = entry
 
     # cfg5-style: every rank has its own volume's labels; Dice counts all-reduced must equal the sum of the oracle's
@@ -94,10 +101,40 @@ def main() -> None:
         results["dice_allreduce_exact"] = bool(np.array_equal(counts.cpu().numpy(), want))
         ok = results["dice_allreduce_exact"] and all(
             v.get("mismatch_vs_single_gpu", 0) == 0 and v.get("mismatch_vs_oracle", 0) == 0 and
-            v.get("block_mismatch_vs_oracle", 0) == 0 and (v.get("p2p_mismatch_vs_oracle") or 0) == 0
+            v.get("block_mismatch_vs_oracle", 0) == 0 and (v.get("p2p_mismatch_vs_oracle") or 0) == 0 and
+            (v.get("flat_mismatch_vs_oracle") or 0) == 0
             for kk, v in results.items() if kk.startswith("case"))
         results["world"] = world
         results["ok"] = ok
+    dist.barrier()
+    return results
+
+
+def summary(results: dict) -> dict:
+    """The block bench.py puts on its JSON line at N > 1."""
+    cases = [v for k, v in results.items() if k.startswith("case")]
+    tot = lambda key: sum(int(c.get(key) or 0) for c in cases)  # noqa: E731
+    return {
+        "checked_against": "CPU oracle (oracle/sliding_window.py) on 4 seeded volumes, labels compared outside top-2 gaps < 1e-5",
+        "world": results.get("world"), "ok": bool(results.get("ok")),
+        "mismatch_vs_oracle": tot("mismatch_vs_oracle") + tot("block_mismatch_vs_oracle") + tot("p2p_mismatch_vs_oracle") +
+        tot("flat_mismatch_vs_oracle"),
+        "slab_nccl": tot("mismatch_vs_oracle"), "block_nccl": tot("block_mismatch_vs_oracle"),
+        "block_p2p": tot("p2p_mismatch_vs_oracle") if any(c.get("p2p_used") for c in cases) else "unavailable",
+        "flat_p2p": tot("flat_mismatch_vs_oracle") if all(c.get("flat_error") is None for c in cases) else
+        [c.get("flat_error") for c in cases if c.get("flat_error")][0],
+        "voxels": sum(c["voxels"] for c in cases), "near_tie_voxels": tot("near_tie_voxels"),
+        "dice_allreduce_exact": results.get("dice_allreduce_exact"),
+    }
+
+
+def main() -> None:
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    results = run_checks(rank, world, dev)
+    if rank == 0:
         print(json.dumps(results))
     dist.barrier()
     dist.destroy_process_group()

@@ -17,9 +17,16 @@ def test_reference_arm_json_contract():
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "windows" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "oracle" in cb["sample"]
     assert line["config"]["workload"] == "cfg1" and line["config"]["shape"] == [1, 1, 128, 128, 128]
     assert line["gpu_launches"] == 0 and line["vs_baseline"] is None and line["dtype"] == "f32"
+    # both arms print the same config dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+    ours = bench.config_dict(argparse.Namespace(workload="cfg1", sw_batch=8), bench.WORKLOADS["cfg1"])
+    assert ours == line["config"] and line["config"]["windows"] == 8
 
 
 def test_reference_arm_other_ranks_exit_quietly():
