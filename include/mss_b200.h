@@ -257,6 +257,16 @@ int mss_flip_copy(const float* in, float* out, int64_t n_outer, const int32_t di
 int mss_mirror_merge(const float* const* preds, const int32_t* mirror_masks, int32_t n_terms, float scale,
                      float* out, int64_t n_outer, const int32_t dims[3], void* stream);
 
+/* Half-precision aggregation of the tiler's `all_in_gpu` branch (neural_network.py:346-372, :399-406, :420-423): importance
+ * map, aggregated results and counts are binary16 there.  batch_ptrs[i] -> fp32 [sw_batch, K, roi] tile predictions (the
+ * output of mss_mirror_merge, NOT yet weighted), ALL windows of `lay` in one call; importance_map_half_valued is the fp32 copy
+ * of the map after `.half()` (every value exactly representable in binary16).  Per voxel and class, in tile order:
+ * agg = half(float(agg) + float(half(pred * w))), nb = half(float(nb) + w); probs_out[Nb, K, extent, pitch_w] receives
+ * float(half(agg / nb)) and labels (optional) the first-max argmax. */
+int mss_accumulate_half(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
+                        const float* importance_map_half_valued, float* probs_out, uint8_t* labels, int32_t label_pitch_w,
+                        void* stream);
+
 /* ---- 95th-percentile Hausdorff distance (engine/test.py:31,55-57) -------- */
 
 /* Surface voxels of class `cls` inside the box [box_lo, box_hi) of a uint8 label map [dims] (MONAI

@@ -113,9 +113,11 @@ def predict_3D_tiled(x: torch.Tensor, network: Callable[[torch.Tensor], torch.Te
                      step_size: float = 0.5, do_mirroring: bool = True, mirror_axes: Sequence[int] = (0, 1, 2),
                      use_gaussian: bool = True, nonlin: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                      sw_batch_size: int = 1, stats: Optional[InferStats] = None,
-                     group_bytes: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``_internal_predict_3D_3Dconv_tiled`` (neural_network.py:300-437, the float32 branch): ``x`` is ``[C, X, Y, Z]``;
-    returns ``(segmentation uint8 [X, Y, Z], class_probabilities fp32 [K, X, Y, Z])`` as CUDA tensors.
+                     group_bytes: Optional[int] = None, all_in_gpu: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``_internal_predict_3D_3Dconv_tiled`` (neural_network.py:300-437): ``x`` is ``[C, X, Y, Z]``; returns
+    ``(segmentation uint8 [X, Y, Z], class_probabilities [K, X, Y, Z])`` as CUDA tensors - fp32 probabilities for the
+    default branch, float16 for ``all_in_gpu=True`` (:346-372, :399-406, :420-423: half importance map, half aggregated
+    results and counts, half division; ``mss_accumulate_half`` reproduces every rounding).
 
     ``sw_batch_size`` windows share one backbone call (the reference runs one; results are identical per window)."""
     if not torch.cuda.is_available():
@@ -137,6 +139,8 @@ def predict_3D_tiled(x: torch.Tensor, network: Callable[[torch.Tensor], torch.Te
         else:
             imp = torch.ones(patch, dtype=torch.float32, device=dev)
         predictor = MirrorTTA(network, mirror_axes, do_mirroring, nonlin)
+        if all_in_gpu:
+            return _predict_half(vol, grid, plan, imp, predictor, use_gaussian and num_tiles > 1, sw_batch_size, stats)
         st = Stitcher(plan, imp, fuse=_lib.FUSE_LOGITS, sw_batch=sw_batch_size, group_bytes=group_bytes, stats=stats)
         if stats is not None:
             stats.n_windows = st.total
@@ -151,3 +155,39 @@ def predict_3D_tiled(x: torch.Tensor, network: Callable[[torch.Tensor], torch.Te
         if stats is not None:
             stats.gpu_launches += predictor.gpu_launches
     return _crop(labels, grid)[0], _crop(st.acc, grid)[0]
+
+
+def _predict_half(vol: torch.Tensor, grid: Any, plan: StitchPlan, imp: torch.Tensor, predictor: MirrorTTA, gaussian: bool,
+                  sw_batch_size: int, stats: Optional[InferStats]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The ``all_in_gpu`` branch: every tile's prediction is kept (fp32, as the mirror merge leaves it) and ONE launch of
+    ``mss_accumulate_half`` walks them per voxel in tile order with the reference's binary16 roundings."""
+    lib = _lib.load()
+    dev = vol.device
+    if gaussian:
+        imp_h = imp.half()  # neural_network.py:352-356
+        imp_h[imp_h == 0] = imp_h[imp_h != 0].min()
+        imp = imp_h.float().contiguous()
+    n_batches = -(-plan.n_local // sw_batch_size)
+    if n_batches > _lib.MAX_BATCH_PTRS:
+        sw_batch_size = -(-plan.n_local // _lib.MAX_BATCH_PTRS)
+    st = Stitcher(plan, imp, fuse=_lib.FUSE_LOGITS, sw_batch=sw_batch_size, stats=stats)
+    if stats is not None:
+        stats.n_windows = st.total
+    vol_r = _tma_ready(vol, grid, 0.0)
+    preds: List[torch.Tensor] = []
+    for _first, _n, patches, _centers in st.batches(vol_r, 0.0, grid.pad_lo):
+        preds.append(predictor(patches).to(torch.float32).contiguous())
+        if stats is not None:
+            stats.n_predictor_calls += 1
+    k = int(preds[0].shape[1])
+    lay = plan.layout(k)
+    ext = plan.extent
+    probs = torch.empty((1, k, ext[0], ext[1], plan.pitch_w), dtype=torch.float32, device=dev)
+    labels = torch.empty((1,) + tuple(ext), dtype=torch.uint8, device=dev)
+    ptrs = (C.c_void_p * len(preds))(*[t.data_ptr() for t in preds])
+    rc = lib.mss_accumulate_half(C.byref(lay), ptrs, len(preds), sw_batch_size, imp.data_ptr(), probs.data_ptr(),
+                                 labels.data_ptr(), ext[2], torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_accumulate_half")
+    if stats is not None:
+        stats.gpu_launches += 1 + predictor.gpu_launches
+    return _crop(labels, grid)[0], _crop(probs, grid)[0].to(torch.float16)

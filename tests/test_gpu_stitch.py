@@ -282,9 +282,11 @@ def test_nnunet_tiled_predictor_bit_exact(name, sw_batch):
     st = mss.InferStats()
     with torch.no_grad():
         seg, probs = N.predict_3D_tiled(vol, PositionalPredictor(c["k"], c["patch"]), c["patch"], c["step"], c["mirror"],
-                                        tuple(c["axes"]), c["gaussian"], nonlin=lambda t: t, sw_batch_size=sw_batch, stats=st)
-    assert probs.dtype == torch.float32 and seg.dtype == torch.uint8
-    assert torch.equal(probs.cpu(), torch.from_numpy(fx["probs"]))
+                                        tuple(c["axes"]), c["gaussian"], nonlin=lambda t: t, sw_batch_size=sw_batch, stats=st,
+                                        all_in_gpu=c.get("all_in_gpu", False))
+    # all_in_gpu=True: the reference's half-precision branch (half importance map / aggregated results / counts / division)
+    assert probs.dtype == (torch.float16 if c.get("all_in_gpu") else torch.float32) and seg.dtype == torch.uint8
+    assert torch.equal(probs.float().cpu(), torch.from_numpy(fx["probs"]))
     assert np.array_equal(seg.cpu().numpy(), fx["seg"])
     assert st.gpu_launches > 0
 
