@@ -548,10 +548,14 @@ int launch_cells(const mss_layout_t* lay, const AccParams& p, int logits_dtype, 
     // CTA columns: consecutive tiles, as even as possible, each <= 64 quads and <= kCellMaxTiles tiles
     const int total_q = q_hi - q_lo;
     const int want_cols = (total_q + 63) / 64;
+    static const int cols_mode = getenv("MSS_ACC_COLS") ? atoi(getenv("MSS_ACC_COLS")) : 0;  // tuning knob: 1 = a column per tile
     int n_col = 0;
     for (int w = 0; w < n_wt;) {
         if (n_col >= kCellMaxSeg) return -1;
-        const int target = (total_q + want_cols - 1) / want_cols;
+        // few classes: a column per W tile (the launch is latency-bound and every lane of a warp then runs the same window
+        // list and copy path); many classes: whole rows per CTA, so the pieces of a logits row are fetched together
+        const bool per_tile = cols_mode == 1 || (cols_mode == 0 && g.K <= 4);
+        const int target = per_tile ? 1 : (total_q + want_cols - 1) / want_cols;
         int nq = 0, ntile = 0;
         while (w + ntile < n_wt && ntile < kCellMaxTiles && (ntile == 0 || nq + cp.wt_nq[w + ntile] <= (target > 64 ? 64 : target)) &&
                nq + cp.wt_nq[w + ntile] <= kCellMaxColQuads) {
