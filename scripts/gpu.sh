@@ -12,8 +12,11 @@ case "$what" in
   tests)    python -m pytest tests -m gpu -q -x "$@" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log ;;
   bench)    python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.log; echo "bench rc=$?"; cat gpurun_out/bench.json ;;
   kbench)   python benchmarks/kernel_bench.py "$@" > gpurun_out/kbench.log 2>&1; echo "kbench rc=$?"; tail -40 gpurun_out/kbench.log ;;
-  launches) python bench.py "$@" > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
-              --log-file gpurun_out/launches.csv python bench.py "$@" > gpurun_out/ncu_launches.log 2>&1; echo "launches rc=$?" ;;
+  launches) # a step of the default workload is ~27 000 launches and ncu costs ~25 ms per profiled launch: profile a WINDOW
+            # (LAUNCH_SKIP / LAUNCH_COUNT), e.g. the second half of the timed step incl. its accumulate launch
+            python bench.py "$@" > /dev/null 2>&1 && timeout 1100 ncu --metrics gpu__time_duration.sum --clock-control none \
+              -s ${LAUNCH_SKIP:-40504} -c ${LAUNCH_COUNT:-13503} --csv --log-file gpurun_out/launches.csv python bench.py "$@" \
+              > gpurun_out/ncu_launches.log 2>&1; echo "launches rc=$?" ;;
   ncu)      name=$1; rx=$2; sk=$3; ct=$4; shift 5
             "$@" > gpurun_out/plain_$name.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on \
               -k "regex:$rx" -s $sk -c $ct -f -o gpurun_out/$name "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?" ;;
