@@ -231,8 +231,8 @@ def main():
         report("hausdorff: mask_edges (1 class, whole volume)", 2 * v, med, mn, "u8 in, u8 out")
         e8 = _edges(lab, 1, (0, 0, 0), (d, h, w))
         med, mn = timed(lambda: squared_edt(e8), args.reps, flush)
-        report("hausdorff: exact squared EDT (3 passes + transpose)", 3 * 16 * v + 8 * v - 3 * v, med, mn,
-               "per pass: in + out + two stack arrays, int32 (first pass reads the uint8 surface)")
+        report("hausdorff: exact squared EDT (row scan + 2 envelope passes)", v * (1 + 4 + 4 + 4) + 2 * v * (4 + 4), med, mn,
+               "row scan: mask + left distance round trip + out; envelope pass: in + out (stack traffic not counted: pushes only)")
 
     if want("hausdorff_api"):
         # the whole metric as engine/test.py:55 calls it: K classes, blocky label maps, the prediction a shifted copy
@@ -242,7 +242,7 @@ def main():
         pr = torch.roll(gt, shifts=(2, -3, 1), dims=(0, 1, 2))
         del zz, yy, xx
         med, mn = timed(lambda: mss.hausdorff_distance(pr, gt, k), max(1, args.reps // 2), flush)
-        report(f"hausdorff_distance API, K={k} (host-driven, {k} x 2 EDTs)", 2 * k * 56 * v, med, mn,
+        report(f"hausdorff_distance API, K={k} (device-driven, {k} x 2 EDTs)", 2 * k * 56 * v, med, mn,
                "nominal bytes: 2K full-volume EDTs; boxes are the whole volume for these labels")
 
     if want("loss"):

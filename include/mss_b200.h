@@ -269,6 +269,25 @@ int mss_accumulate_half(const mss_layout_t* lay, const void* const* batch_ptrs, 
 
 /* ---- 95th-percentile Hausdorff distance (engine/test.py:31,55-57) -------- */
 
+/* Bounding boxes of (pred == c) | (label == c) for every class c < n_classes (<= 32) of two uint8 label maps [dims] in one
+ * pass (MONAI generate_spatial_bounding_box per class inside get_mask_edges).  boxes_out: device int32 [n_classes][6] =
+ * {lo_d, lo_h, lo_w, hi_d, hi_h, hi_w} (hi exclusive), which the caller initialises to {2^30, 2^30, 2^30, 0, 0, 0}: a
+ * class in neither map keeps lo > hi. */
+int mss_class_boxes(const uint8_t* pred, const uint8_t* label, const int32_t dims[3], int32_t n_classes,
+                    int32_t* boxes_out, void* stream);
+
+/* Two order statistics of (a masked subset of) a 32-bit array on the device, without a sort and without a host sync:
+ * three radix-histogram levels (11 + 11 + 10 bits).  keys: n_elems values, key_kind 0 = unsigned / non-negative int32 as
+ * stored, 1 = float32 (mapped to order-preserving unsigned); mask (optional uint8, non-zero = take part).  rank_mode 0:
+ * the k_lo-th and k_hi-th smallest (0-based) of the valid elements; rank_mode 1: the two neighbours numpy.percentile
+ * (linear) interpolates for quantile `quant` in [0, 1]: floor((n - 1) * quant) and the next one, n = valid count.
+ * scratch: mss_select_scratch_bytes() of device memory (8-byte aligned); out (device, uint64[4]) = {n, key_lo, key_hi,
+ * key_max} in the mapped unsigned domain.  Behind np.percentile at engine/test.py:55-57 (HD95) and
+ * data/dataset_builder.py:343-353 (ScaleIntensityRangePercentiles). */
+int64_t mss_select_scratch_bytes(void);
+int mss_select2(const void* keys, int32_t key_kind, const uint8_t* mask, int64_t n_elems, int32_t rank_mode, double quant,
+                int64_t k_lo, int64_t k_hi, void* scratch, unsigned long long* out, void* stream);
+
 /* Surface voxels of class `cls` inside the box [box_lo, box_hi) of a uint8 label map [dims] (MONAI
  * get_mask_edges: binary_erosion XOR mask on the bounding box of pred | gt; outside the box = background; axes
  * along which the box is one voxel thick are ignored, as the reference squeezes them away).  Writes
@@ -284,8 +303,13 @@ int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, co
 int mss_edt_pass(const int32_t* in, int32_t* out, int32_t* scratch_s, int32_t* scratch_t, const int32_t dims[3],
                  int32_t axis, void* stream);
 
-/* The first pass straight from a uint8 feature mask [dims] (non-zero = feature voxel): saves writing and reading the
- * int32 input volume. */
+/* The first pass along the CONTIGUOUS axis (2) straight from a uint8 feature mask [dims] without an envelope scan: out[x] =
+ * (distance to the nearest non-zero voxel of the same row)^2, 2^29 when the row has none.  One warp per row (ballot scan).
+ * Follow with mss_edt_pass along axes 1 and 0: the result is laid out like the input, no transposes. */
+int mss_edt_row_mask(const uint8_t* mask, int32_t* out, const int32_t dims[3], void* stream);
+
+/* The first pass straight from a uint8 feature mask [dims] (non-zero = feature voxel) along any axis: saves writing and
+ * reading the int32 input volume. */
 int mss_edt_pass_mask(const uint8_t* mask, int32_t* out, int32_t* scratch_s, int32_t* scratch_t,
                       const int32_t dims[3], int32_t axis, void* stream);
 

@@ -63,8 +63,12 @@ _SIGNATURES = {
     "mss_flip_copy": (C.c_int, [vp, vp, c_i64, I3, c_i32, vp]),
     "mss_mirror_merge": (C.c_int, [C.POINTER(vp), C.POINTER(c_i32), c_i32, c_f32, vp, c_i64, I3, vp]),
     "mss_accumulate_half": (C.c_int, [C.POINTER(Layout), C.POINTER(vp), c_i32, c_i32, vp, vp, vp, c_i32, vp]),
+    "mss_class_boxes": (C.c_int, [vp, vp, I3, c_i32, vp, vp]),
+    "mss_select_scratch_bytes": (c_i64, []),
+    "mss_select2": (C.c_int, [vp, c_i32, vp, c_i64, c_i32, C.c_double, c_i64, c_i64, vp, vp, vp]),
     "mss_mask_edges": (C.c_int, [vp, I3, c_i32, I3, I3, vp, vp, vp]),
     "mss_edt_pass": (C.c_int, [vp, vp, vp, vp, I3, c_i32, vp]),
+    "mss_edt_row_mask": (C.c_int, [vp, vp, I3, vp]),
     "mss_edt_pass_mask": (C.c_int, [vp, vp, vp, vp, I3, c_i32, vp]),
     "mss_dice_ce_sums": (C.c_int, [vp, c_i64, c_i64, c_i64, c_i32, c_i32, vp, c_i32, c_i32, vp, vp]),
     "mss_intensity_transform": (C.c_int, [vp, vp, c_i64, c_i32, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -73,6 +73,110 @@ MSS_EDT_HD void edt_line_mask(const unsigned char* m, int* out, int* s, int* t, 
     edt_line_fn<Idx>([m, stride](int u) -> long long { return m[u * stride] ? 0 : kEdtInf; }, out, s, t, n, stride);
 }
 
+// The same lower envelope with the TOP of the parabola stack kept in registers: a push spills the old top (one packed
+// position / take-over word into st[], its value into hv[] - two independent stores nobody waits for), only a pop loads
+// (the entry below).  In the common case - the new parabola just joins the envelope - an iteration touches no scratch
+// memory at all, where edt_line_fn pays two dependent round trips (s[q], then h[s[q]]).  Positions and take-over points
+// are < 2^14 (volume sides < 16384), so both fit one 32-bit word.  Same comparisons, same integer arithmetic, same result.
+template <typename Idx, typename HFn>
+MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx stride) {
+    int q = -1;                       // index of the top entry (entries 0 .. q-1 live in st / hv)
+    // 32-bit arithmetic throughout: positions < 2^14, finite values < 2^29, so (x - i)^2 + h < 2^28 + 2^29 < 2^31
+    int ts = 0, tt = 0, th = 0;  // the top: position, take-over point, value
+    constexpr int kAhead = 8;          // line values fetched together: one memory latency per 8 steps, not per step
+    for (int u0 = 0; u0 < n; u0 += kAhead) {
+        int hb[kAhead];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < kAhead; ++k) {
+            const long long v = u0 + k < n ? h(u0 + k) : static_cast<long long>(kEdtInf);
+            hb[k] = v < kEdtInf ? static_cast<int>(v) : kEdtInf;
+        }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < kAhead; ++k) {
+            const int u = u0 + k;
+            const int hu = hb[k];
+            if (hu >= kEdtInf) continue;
+            while (q >= 0) {
+                // parabola u is at or below the top parabola at the point where the top took over: the top never wins
+                if ((tt - ts) * (tt - ts) + th > (tt - u) * (tt - u) + hu) {
+                    --q;
+                    if (q >= 0) {
+                        const int e = st[q * stride];
+                        ts = e & 0xffff;
+                        tt = e >> 16;
+                        th = hv[q * stride];
+                    }
+                } else {
+                    break;
+                }
+            }
+            if (q < 0) {
+                q = 0;
+                ts = u;
+                tt = 0;
+                th = hu;
+            } else {
+                const int num = u * u - ts * ts + hu - th, den = 2 * (u - ts);
+                int w = num >= 0 ? num / den : -((-num + den - 1) / den);  // floor division
+                w += 1;
+                if (w < n) {
+                    st[q * stride] = ts | (tt << 16);
+                    hv[q * stride] = th;
+                    ++q;
+                    ts = u;
+                    tt = w < 0 ? 0 : w;
+                    th = hu;
+                }
+            }
+        }
+    }
+    if (q < 0) {
+        for (int x = 0; x < n; ++x) out[x * stride] = kEdtInf;
+        return;
+    }
+    for (int x = n - 1; x >= 0; --x) {
+        while (q > 0 && tt > x) {
+            --q;
+            const int e = st[q * stride];
+            ts = e & 0xffff;
+            tt = e >> 16;
+            th = hv[q * stride];
+        }
+        const int v = (x - ts) * (x - ts) + th;
+        out[x * stride] = v >= kEdtInf ? kEdtInf : v;
+    }
+}
+
+template <typename Idx>
+MSS_EDT_HD void edt_line_cached(const int* h, int* out, int* st, int* hv, int n, Idx stride) {
+    edt_line_cached_fn<Idx>([h, stride](int u) -> long long { return h[u * stride]; }, out, st, hv, n, stride);
+}
+
+template <typename Idx>
+MSS_EDT_HD void edt_line_mask_cached(const unsigned char* m, int* out, int* st, int* hv, int n, Idx stride) {
+    edt_line_cached_fn<Idx>([m, stride](int u) -> long long { return m[u * stride] ? 0 : kEdtInf; }, out, st, hv, n, stride);
+}
+
+// First pass along a line straight from a feature mask without any envelope: the squared distance to the nearest
+// feature of the SAME line is (distance to the nearest set position)^2.  Host form of the row-scan kernel.
+MSS_EDT_HD void edt_row_from_mask(const unsigned char* m, int* out, int n) {
+    int last = -(1 << 20);
+    for (int x = 0; x < n; ++x) {
+        if (m[x]) last = x;
+        out[x] = x - last;  // distance to the nearest feature on the left (huge when none)
+    }
+    int next = 1 << 20;
+    for (int x = n - 1; x >= 0; --x) {
+        if (m[x]) next = x;
+        const long long d = out[x] < next - x ? out[x] : next - x;
+        out[x] = d >= (1 << 14) ? kEdtInf : static_cast<int>(d * d);
+    }
+}
+
 // Is the voxel at `c` (class `cls`, position (z, y, x) inside a box of n[0] x n[1] x n[2] voxels, strides sz / sy / 1)
 // on the surface of its class?  binary_erosion(mask) XOR mask with scipy's 6-connected structure and border_value 0 on
 // the CROPPED box: a neighbour outside the box is background, and an axis along which the box is one voxel thick does

@@ -69,14 +69,131 @@ __global__ void __launch_bounds__(128) edt_pass_kernel(const __grid_constant__ E
         if (p.axis == 0) o = l;
         else if (p.axis == 1) o = (l / p.n[2]) * sz + (l % p.n[2]);
         else o = l * p.n[2];
-        if (p.mask != nullptr) edt_line_mask<long long>(p.mask + o, p.out + o, p.s + o, p.t + o, len, stride);
-        else edt_line<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride);
+        if (p.mask != nullptr) edt_line_mask_cached<long long>(p.mask + o, p.out + o, p.s + o, p.t + o, len, stride);
+        else edt_line_cached<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride);
+    }
+}
+
+// First EDT pass along the CONTIGUOUS axis straight from a uint8 feature mask: no envelope needed - the squared distance
+// to the nearest feature of the same row.  One warp per row, 32 voxels per step: a ballot of the feature bits gives every
+// lane its nearest set position inside the chunk (clz / ffs on the masked ballot), a carried position covers the chunks
+// before / after.  Forward sweep stores the left distance, backward sweep combines it with the right one and squares.
+__global__ void __launch_bounds__(256) edt_row_mask_kernel(const uint8_t* __restrict__ mask, int* __restrict__ out,
+                                                           long long n_rows, int w) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int chunks = (w + 31) >> 5;
+    constexpr int kFar = 1 << 20;
+    for (long long r = warp; r < n_rows; r += n_warps) {
+        const uint8_t* m = mask + r * w;
+        int* o = out + r * w;
+        int last = -kFar;
+        for (int c = 0; c < chunks; ++c) {
+            const int x = c * 32 + lane;
+            const unsigned bal = __ballot_sync(0xffffffffu, x < w && m[x] != 0);
+            const unsigned le = bal & (0xffffffffu >> (31 - lane));  // features at or left of this lane
+            const int pos = le ? c * 32 + 31 - __clz(le) : last;
+            if (x < w) o[x] = x - pos;
+            if (bal) last = c * 32 + 31 - __clz(bal);
+        }
+        int next = kFar;
+        for (int c = chunks - 1; c >= 0; --c) {
+            const int x = c * 32 + lane;
+            const unsigned bal = __ballot_sync(0xffffffffu, x < w && m[x] != 0);
+            const unsigned ge = bal & (0xffffffffu << lane);  // features at or right of this lane
+            const int pos = ge ? c * 32 + __ffs(ge) - 1 : next;
+            if (x < w) {
+                const int dl = o[x], dr = pos - x;
+                const long long d = dl < dr ? dl : dr;
+                o[x] = d >= (1 << 14) ? kEdtInf : static_cast<int>(d * d);
+            }
+            if (bal) next = c * 32 + __ffs(bal) - 1;
+        }
+    }
+}
+
+// Bounding boxes of (pred == c) | (label == c) for every class c < K in one pass over both label maps
+// (MONAI generate_spatial_bounding_box per class, get_mask_edges): boxes[c] = {lo_d, lo_h, lo_w, hi_d, hi_h, hi_w}
+// (hi exclusive; lo > hi for a class that occurs in neither map).  Shared-memory min / max per CTA, then global atomics.
+constexpr int kBoxMaxClasses = 32;
+
+__global__ void __launch_bounds__(256) class_boxes_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int d, int h,
+                                                          int w, int k, int* __restrict__ boxes) {
+    __shared__ int s_lo[kBoxMaxClasses][3], s_hi[kBoxMaxClasses][3];
+    for (int i = threadIdx.x; i < kBoxMaxClasses * 3; i += blockDim.x) {
+        (&s_lo[0][0])[i] = 1 << 30;
+        (&s_hi[0][0])[i] = -1;
+    }
+    __syncthreads();
+    const long long rows = static_cast<long long>(d) * h;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int z = static_cast<int>(r / h), y = static_cast<int>(r - static_cast<long long>(z) * h);
+        const uint8_t* pa = a + r * w;
+        const uint8_t* pb = b + r * w;
+        unsigned seen = 0;  // classes this thread met in this row, with their W range
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            const unsigned ca = pa[x], cb = pb[x];
+            if (ca < static_cast<unsigned>(k)) {
+                seen |= 1u << ca;
+                atomicMin(&s_lo[ca][2], x);
+                atomicMax(&s_hi[ca][2], x);
+            }
+            if (cb < static_cast<unsigned>(k) && cb != ca) {
+                seen |= 1u << cb;
+                atomicMin(&s_lo[cb][2], x);
+                atomicMax(&s_hi[cb][2], x);
+            }
+        }
+        while (seen) {
+            const int c = __ffs(seen) - 1;
+            seen &= seen - 1;
+            atomicMin(&s_lo[c][0], z);
+            atomicMax(&s_hi[c][0], z);
+            atomicMin(&s_lo[c][1], y);
+            atomicMax(&s_hi[c][1], y);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * 3; i += blockDim.x) {
+        const int c = i / 3, ax = i - c * 3;
+        if (s_hi[c][ax] >= 0) {
+            atomicMin(&boxes[c * 6 + ax], s_lo[c][ax]);
+            atomicMax(&boxes[c * 6 + 3 + ax], s_hi[c][ax] + 1);
+        }
     }
 }
 
 }  // namespace mss
 
 using namespace mss;
+
+extern "C" int mss_class_boxes(const uint8_t* pred, const uint8_t* label, const int32_t dims[3], int32_t n_classes,
+                               int32_t* boxes_out, void* stream) {
+    MSS_REQUIRE(pred && label && dims && boxes_out, MSS_E_ARG, "class_boxes: null argument");
+    MSS_REQUIRE(n_classes > 0 && n_classes <= kBoxMaxClasses, MSS_E_UNSUPPORTED, "class_boxes: n_classes %d outside [1, %d]",
+                n_classes, kBoxMaxClasses);
+    for (int a = 0; a < 3; ++a) MSS_REQUIRE(dims[a] > 0, MSS_E_ARG, "class_boxes: dims must be positive");
+    // boxes_out must hold {2^30, 2^30, 2^30, 0, 0, 0} per class on entry (the caller fills it; min / max are accumulated)
+    long long rows = static_cast<long long>(dims[0]) * dims[1];
+    long long blocks = rows < 148LL * 8 ? rows : 148LL * 8;
+    class_boxes_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(pred, label, dims[0], dims[1], dims[2],
+                                                                                  n_classes, boxes_out);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}
+
+extern "C" int mss_edt_row_mask(const uint8_t* mask, int32_t* out, const int32_t dims[3], void* stream) {
+    MSS_REQUIRE(mask && out && dims, MSS_E_ARG, "edt_row_mask: null argument");
+    for (int a = 0; a < 3; ++a)
+        MSS_REQUIRE(dims[a] > 0 && dims[a] < (1 << 14), MSS_E_UNSUPPORTED, "edt_row_mask: dims must be in [1, 16384)");
+    const long long rows = static_cast<long long>(dims[0]) * dims[1];
+    long long blocks = (rows + 7) / 8;  // 8 warps (rows) per CTA
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    edt_row_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(mask, out, rows, dims[2]);
+    MSS_CUDA(cudaGetLastError());
+    return MSS_OK;
+}
 
 extern "C" int mss_mask_edges(const uint8_t* labels, const int32_t dims[3], int32_t cls, const int32_t box_lo[3],
                               const int32_t box_hi[3], uint8_t* edges_out, int32_t* edt_input_out, void* stream) {

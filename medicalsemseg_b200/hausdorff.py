@@ -5,8 +5,10 @@ uint8 label maps instead of one-hot tensors.
 
 Per class: bounding box of pred | gt, surface voxels of both masks (``mss_mask_edges``), the exact squared Euclidean
 distance transform of each surface (three ``mss_edt_pass`` launches), the distances at the other surface's voxels,
-float64 sqrt and NumPy's linear-interpolation percentile.  Box search, transposes, boolean gathers and the sort are torch
-plumbing; the two stencil / scan kernels are libmss_b200.so."""
+float64 sqrt and NumPy's linear-interpolation percentile.  Round 2: everything data-sized runs in libmss_b200.so kernels -
+``mss_class_boxes`` (all boxes in one pass), ``mss_mask_edges``, ``mss_edt_row_mask`` + ``mss_edt_pass`` x 2,
+``mss_select2`` (the order statistics np.percentile interpolates, by radix histograms masked with the surface: no boolean
+gather, no sort) - with one host sync for the boxes and one device-to-host copy of the results."""
 from __future__ import annotations
 
 from typing import Any, Optional, Tuple
@@ -15,19 +17,6 @@ import numpy as np
 import torch
 
 from . import _lib
-
-
-def _bbox(mask: torch.Tensor) -> Optional[Tuple[Tuple[int, int, int], Tuple[int, int, int]]]:
-    """``generate_spatial_bounding_box`` of a boolean volume (None when empty)."""
-    lo, hi = [], []
-    for a in range(3):
-        other = tuple(x for x in range(3) if x != a)
-        idx = torch.nonzero(mask.any(dim=other)).flatten()
-        if idx.numel() == 0:
-            return None
-        lo.append(int(idx[0]))
-        hi.append(int(idx[-1]) + 1)
-    return tuple(lo), tuple(hi)
 
 
 def _edges(labels: torch.Tensor, cls: int, lo, hi) -> torch.Tensor:
@@ -41,10 +30,11 @@ def _edges(labels: torch.Tensor, cls: int, lo, hi) -> torch.Tensor:
 
 
 def squared_edt(feature: torch.Tensor) -> torch.Tensor:
-    """Exact squared distance to the nearest non-zero voxel of the uint8 volume ``feature`` (int32; 2**29 when there is
-    none), returned in the TRANSPOSED layout ``[D, W, H]``: the pass along the contiguous axis runs on a transposed copy
-    so its line loop is coalesced too.  An int32 ``feature`` is taken as the transform's input itself (0 on features,
-    2**29 elsewhere)."""
+    """Exact squared distance to the nearest non-zero voxel of the uint8 volume ``feature`` (int32 ``[D, H, W]``; 2**29 when
+    there is none).  Pass along W: one ballot scan per row straight from the mask (``mss_edt_row_mask``, no envelope);
+    passes along H and D: the lower envelope of parabolas per line with the stack top in registers (``mss_edt_pass``),
+    consecutive threads on lines that are adjacent in memory - no transposes.  An int32 ``feature`` is taken as the
+    transform's input itself (0 on features, 2**29 elsewhere) and takes three envelope passes."""
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
     d, h, w = feature.shape
@@ -52,59 +42,81 @@ def squared_edt(feature: torch.Tensor) -> torch.Tensor:
     t2, s, t = torch.empty_like(t1), torch.empty_like(t1), torch.empty_like(t1)
     dims = _lib.I3(d, h, w)
     if feature.dtype == torch.uint8:
-        rc = lib.mss_edt_pass_mask(feature.contiguous().data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 0, stream)
+        _lib.check(lib.mss_edt_row_mask(feature.contiguous().data_ptr(), t1.data_ptr(), dims, stream), "mss_edt_row_mask")
     else:
-        rc = lib.mss_edt_pass(feature.contiguous().data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 0, stream)
-    _lib.check(rc, "mss_edt_pass")
+        _lib.check(lib.mss_edt_pass(feature.contiguous().data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 2, stream),
+                   "mss_edt_pass")
     _lib.check(lib.mss_edt_pass(t1.data_ptr(), t2.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 1, stream), "mss_edt_pass")
-    at = t2.transpose(1, 2).contiguous()  # [D, W, H]
-    bt = torch.empty_like(at)
-    _lib.check(lib.mss_edt_pass(at.data_ptr(), bt.data_ptr(), s.data_ptr(), t.data_ptr(), _lib.I3(d, w, h), 1, stream),
-               "mss_edt_pass")
-    return bt
+    _lib.check(lib.mss_edt_pass(t2.data_ptr(), t1.data_ptr(), s.data_ptr(), t.data_ptr(), dims, 0, stream), "mss_edt_pass")
+    return t1
 
 
-def _np_percentile(sorted_vals: torch.Tensor, q: float) -> float:
-    """``numpy.percentile(x, q)`` (linear) of an ascending float64 CUDA vector, NumPy's own arithmetic (incl. inf - inf)."""
-    n = sorted_vals.numel()
-    quant = q / 100.0
-    pos = (n - 1) * quant  # numpy's virtual index for method='linear'
-    if pos >= n - 1:
-        lo = hi = n - 1
-    elif pos < 0:
-        lo = hi = 0
-    else:
-        lo = int(np.floor(pos))
-        hi = lo + 1
-    t = pos - np.floor(pos)
-    a, b = float(sorted_vals[lo]), float(sorted_vals[hi])
+def _np_lerp(a: float, b: float, n: int, q: float) -> float:
+    """``numpy.percentile(x, q)`` (method 'linear') from the two order statistics it interpolates: ``a`` = x_sorted[lo],
+    ``b`` = x_sorted[hi] with lo = floor((n - 1) q / 100), hi = min(lo + 1, n - 1).  NumPy's own arithmetic (``_lerp``,
+    incl. inf - inf = nan)."""
+    pos = (n - 1) * (q / 100.0)
+    t = pos - np.floor(pos) if 0 <= pos < n - 1 else 0.0
     with np.errstate(invalid="ignore"):
         d = np.float64(b) - np.float64(a)
         return float(np.float64(b) - d * (1.0 - t)) if t >= 0.5 else float(np.float64(a) + d * t)
 
 
-def _percent_distance(edges_from: torch.Tensor, edges_to: torch.Tensor, percentile: Optional[float]) -> float:
-    """``compute_percent_hausdorff_distance(edges_from, edges_to)``: distances from the voxels of one surface to the other."""
-    n_from, n_to = int(edges_from.sum()), int(edges_to.sum())
+_INF_KEY = 1 << 29  # squared_edt's "no feature" value
+
+
+def _directed_async(edges_from: torch.Tensor, edges_to: torch.Tensor, quant: float, out_row: torch.Tensor, scratch: torch.Tensor,
+                    n_to_slot: torch.Tensor) -> None:
+    """Everything of ``compute_percent_hausdorff_distance(edges_from, edges_to)`` that needs the GPU, enqueued without a host
+    sync: the exact squared distance transform of ``edges_to`` and the two order statistics of its values at the voxels of
+    ``edges_from`` (``mss_select2``: radix histograms masked by the surface; ranks derived on the device from the surface's
+    voxel count).  ``out_row`` (uint64[4]) receives {n_from, d2_lo, d2_hi, d2_max}, ``n_to_slot`` the voxel count of
+    ``edges_to``."""
+    lib = _lib.load()
+    dt = squared_edt(edges_to)
+    n_to_slot.copy_(edges_to.sum(dtype=torch.int64))
+    rc = lib.mss_select2(dt.data_ptr(), 0, edges_from.data_ptr(), dt.numel(), 1, float(quant), 0, 0, scratch.data_ptr(),
+                         out_row.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_select2")
+
+
+def _directed_value(row: np.ndarray, n_to: int, percentile: Optional[float]) -> float:
+    """The host side of one direction, from the numbers the device produced (get_surface_distance's special cases included)."""
+    n_from, k_lo, k_hi, k_max = (int(v) for v in row)
     inf = float("inf")
-    if n_to == 0:      # get_surface_distance: `dis = inf * ones; return dis[seg_pred]`
-        dist = torch.full((n_from,), inf, dtype=torch.float64, device=edges_from.device)
-    elif n_from == 0:  # ... `if not np.any(seg_pred): return dis[seg_gt]` - infinities for the OTHER surface's voxels
-        dist = torch.full((n_to,), inf, dtype=torch.float64, device=edges_from.device)
+    if n_to == 0:      # `dis = inf * ones; return dis[seg_pred]`: n_from infinities
+        n, a, b, mx = n_from, inf, inf, inf
+    elif n_from == 0:  # `if not np.any(seg_pred): return dis[seg_gt]`: infinities for the OTHER surface's voxels
+        n, a, b, mx = n_to, inf, inf, inf
     else:
-        dt_t = squared_edt(edges_to)             # [D, W, H]
-        dist = dt_t[edges_from.transpose(1, 2).bool()].to(torch.float64).sqrt()
-    if dist.numel() == 0:
-        return float("nan")                      # surface_distance.shape == (0,)
+        n = n_from
+        a, b, mx = (inf if k >= _INF_KEY else float(np.sqrt(np.float64(k))) for k in (k_lo, k_hi, k_max))
+    if n == 0:
+        return float("nan")  # surface_distance.shape == (0,)
     if not percentile:
-        return float(dist.max())
-    return _np_percentile(torch.sort(dist).values, float(percentile))
+        return mx
+    return _np_lerp(a, b, n, float(percentile))
+
+
+def class_boxes(pred: torch.Tensor, label: torch.Tensor, n_classes: int) -> np.ndarray:
+    """``generate_spatial_bounding_box`` of ``(pred == c) | (label == c)`` for every class in ONE launch and one D2H:
+    int32 ``[K, 6]`` = lo (3) then hi (3, exclusive); lo > hi where the class occurs in neither map."""
+    lib = _lib.load()
+    boxes = torch.tensor([[1 << 30] * 3 + [0] * 3] * n_classes, dtype=torch.int32, device=pred.device)
+    rc = lib.mss_class_boxes(pred.data_ptr(), label.data_ptr(), _lib.I3(*pred.shape), int(n_classes), boxes.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_class_boxes")
+    return boxes.cpu().numpy()
 
 
 def hausdorff_distance(pred: torch.Tensor, label: torch.Tensor, n_classes: int, percentile: Optional[float] = 95,
                        include_background: bool = True, directed: bool = False) -> np.ndarray:
     """Per-class (percentile) Hausdorff distance in voxels, float64 ``[K]`` (``[K-1]`` without background): NaN when a
-    class is absent from both maps, inf / NaN by NumPy's rules when it is absent from one."""
+    class is absent from both maps, inf / NaN by NumPy's rules when it is absent from one.
+
+    Device-driven: one launch finds every class's bounding box (the only host sync before the end), then per class the
+    surfaces, the two distance transforms and the order statistics are enqueued back to back; the percentile arithmetic
+    runs on the host from ONE device-to-host copy of 2 x 5 integers per class."""
     if not (pred.is_cuda and label.is_cuda):
         raise _lib.MssError("hausdorff_distance needs CUDA tensors; there is no CPU fallback")
     p = pred.reshape(pred.shape[-3:]).to(torch.uint8).contiguous()
@@ -112,22 +124,37 @@ def hausdorff_distance(pred: torch.Tensor, label: torch.Tensor, n_classes: int, 
     y = (y if y.dtype == torch.uint8 else y.round().clamp(0, 255).to(torch.uint8)).contiguous()
     if p.shape != y.shape:
         raise ValueError(f"pred {tuple(p.shape)} and label {tuple(y.shape)} differ")
-    out = []
+    lib = _lib.load()
+    classes = list(range(0 if include_background else 1, n_classes))
+    quant = (float(percentile) / 100.0) if percentile else 1.0
     with torch.cuda.device(p.device):
-        for c in range(0 if include_background else 1, n_classes):
-            box = _bbox((p == c) | (y == c))
-            if box is None:
-                out.append(float("nan"))
+        boxes = class_boxes(p, y, n_classes)
+        res = torch.zeros((len(classes), 2, 4), dtype=torch.int64, device=p.device)   # uint64 bit patterns (values < 2^63)
+        n_to = torch.zeros((len(classes), 2), dtype=torch.int64, device=p.device)
+        scratch = torch.empty(int(lib.mss_select_scratch_bytes()) // 8 + 1, dtype=torch.int64, device=p.device)
+        present = []
+        for i, c in enumerate(classes):
+            lo, hi = tuple(int(v) for v in boxes[c, :3]), tuple(int(v) for v in boxes[c, 3:])
+            present.append(all(h > l for l, h in zip(lo, hi)))
+            if not present[-1]:
                 continue
-            lo, hi = box
             ep = _edges(p, c, lo, hi)
             ey = _edges(y, c, lo, hi)
-            d1 = _percent_distance(ep, ey, percentile)
-            if directed:
-                out.append(d1)
-                continue
-            d2 = _percent_distance(ey, ep, percentile)
-            out.append(max(d1, d2))               # Python's max, as the reference calls it (NaN handling included)
+            _directed_async(ep, ey, quant, res[i, 0], scratch, n_to[i, 0])
+            if not directed:
+                _directed_async(ey, ep, quant, res[i, 1], scratch, n_to[i, 1])
+        res_h, n_to_h = res.cpu().numpy(), n_to.cpu().numpy()
+    out = []
+    for i, _c in enumerate(classes):
+        if not present[i]:
+            out.append(float("nan"))
+            continue
+        d1 = _directed_value(res_h[i, 0], int(n_to_h[i, 0]), percentile)
+        if directed:
+            out.append(d1)
+            continue
+        d2 = _directed_value(res_h[i, 1], int(n_to_h[i, 1]), percentile)
+        out.append(max(d1, d2))                   # Python's max, as the reference calls it (NaN handling included)
     return np.asarray(out, dtype=np.float64)
 
 

@@ -92,15 +92,27 @@ def normalize_intensity(img: torch.Tensor, subtrahend: Optional[float] = None, d
 
 
 def percentile(img: torch.Tensor, q: float) -> float:
-    """``numpy.percentile(img, q)`` (linear interpolation between order statistics) of a CUDA tensor."""
-    flat = img.reshape(-1).to(torch.float32)
+    """``numpy.percentile(img, q)`` (linear interpolation between order statistics) of a CUDA tensor: the two order
+    statistics come from ``mss_select2`` (three radix-histogram passes over the float32 voxels, no sort)."""
+    lib = _lib.load()
+    flat = img.reshape(-1).to(torch.float32).contiguous()
     n = flat.numel()
     pos = (n - 1) * (float(q) / 100.0)
     lo = int(np.floor(pos))
     hi = min(lo + 1, n - 1)
     t = pos - lo
-    a = float(torch.kthvalue(flat, lo + 1).values)
-    b = float(torch.kthvalue(flat, hi + 1).values)
+    with torch.cuda.device(flat.device):
+        out = torch.zeros(4, dtype=torch.int64, device=flat.device)
+        scratch = torch.empty(int(lib.mss_select_scratch_bytes()) // 8 + 1, dtype=torch.int64, device=flat.device)
+        rc = lib.mss_select2(flat.data_ptr(), 1, None, n, 0, 0.0, lo, hi, scratch.data_ptr(), out.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "mss_select2")
+        keys = out.cpu().numpy()
+    def unmap(k: int) -> float:  # inverse of the order-preserving float32 -> uint32 map
+        u = np.uint32(k)
+        u = np.uint32(u & np.uint32(0x7FFFFFFF)) if (u & np.uint32(0x80000000)) else np.uint32(~u)
+        return float(np.frombuffer(np.uint32(u).tobytes(), dtype=np.float32)[0])
+    a, b = unmap(int(keys[1])), unmap(int(keys[2]))
     d = b - a
     return float(b - d * (1.0 - t)) if t >= 0.5 else float(a + d * t)  # numpy's _lerp
 

@@ -104,6 +104,25 @@ extern "C" void host_edt_squared(const uint8_t* feature, int d, int h, int w, in
     for (long long i = 0; i < n; ++i) out[i] = b[i];
 }
 
+// the order and the routines the GPU driver uses since round 2: row scan along W from the mask, then the envelope with
+// the register-cached stack top along H and D
+extern "C" void host_edt_squared_v2(const uint8_t* feature, int d, int h, int w, int* out) {
+    const long long n = static_cast<long long>(d) * h * w;
+    std::vector<int> a(n), b(n), s(n), t(n);
+    for (long long r = 0; r < static_cast<long long>(d) * h; ++r) mss::edt_row_from_mask(feature + r * w, a.data() + r * w, w);
+    for (int z = 0; z < d; ++z)
+        for (int x = 0; x < w; ++x) {
+            const long long o = static_cast<long long>(z) * h * w + x;
+            mss::edt_line_cached<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, h, w);
+        }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const long long o = static_cast<long long>(y) * w + x;
+            mss::edt_line_cached<long long>(b.data() + o, a.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w);
+        }
+    for (long long i = 0; i < n; ++i) out[i] = a[i];
+}
+
 // surface voxels of class cls inside the box [lo, hi) of a label map [dims], as csrc/hausdorff.cu computes them
 extern "C" void host_mask_edges(const uint8_t* labels, const int* dims, int cls, const int* lo, const int* hi, uint8_t* edges) {
     const int n[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};

@@ -76,7 +76,8 @@ def test_dice_chunks_uniform_volume(lib):
 
 
 @pytest.mark.parametrize("shape,density", [((9, 11, 13), 0.05), ((20, 7, 15), 0.01), ((1, 16, 16), 0.1), ((12, 12, 1), 0.3),
-                                           ((17, 19, 23), 0.002), ((8, 8, 8), 1.0), ((6, 5, 4), 0.0), ((30, 3, 31), 0.03)])
+                                           ((17, 19, 23), 0.002), ((8, 8, 8), 1.0), ((6, 5, 4), 0.0), ((30, 3, 31), 0.03),
+                                           ((5, 6, 70), 0.02), ((40, 33, 37), 0.0005)])
 def test_edt_line_routine_matches_scipy(lib, shape, density):
     """csrc/edt.cuh (the routine the GPU pass kernel runs per line) applied along the three axes on the host: exact
     squared distances, i.e. scipy.ndimage.distance_transform_edt squared."""
@@ -85,6 +86,10 @@ def test_edt_line_routine_matches_scipy(lib, shape, density):
     feat = (rs.random_sample(shape) < density).astype(np.uint8)
     out = np.zeros(shape, np.int32)
     lib.host_edt_squared(feat.ctypes.data, shape[0], shape[1], shape[2], out.ctypes.data)
+    # round 2: row scan from the mask + the envelope with the register-cached stack top (what the GPU driver runs now)
+    out2 = np.zeros(shape, np.int32)
+    lib.host_edt_squared_v2(feat.ctypes.data, shape[0], shape[1], shape[2], out2.ctypes.data)
+    assert np.array_equal(out, out2)
     if feat.sum() == 0:
         assert np.all(out == 1 << 29)
         return

@@ -385,10 +385,10 @@ def test_squared_edt_matches_scipy_and_properties():
     for shape, dens in [((33, 20, 41), 0.01), ((8, 64, 8), 0.2), ((50, 50, 50), 0.0005)]:
         feat = rs.random_sample(shape) < dens
         h0 = torch.from_numpy(np.where(feat, 0, 1 << 29).astype(np.int32)).cuda()
-        got = squared_edt(h0).transpose(1, 2).cpu().numpy()
+        got = squared_edt(h0).cpu().numpy()
         want = ndimage.distance_transform_edt(~feat)
         assert np.array_equal(np.sqrt(got.astype(np.float64)), want)
-        got8 = squared_edt(torch.from_numpy(feat.astype(np.uint8)).cuda()).transpose(1, 2).cpu().numpy()  # mask-direct first pass
+        got8 = squared_edt(torch.from_numpy(feat.astype(np.uint8)).cuda()).cpu().numpy()  # row scan from the mask first
         assert np.array_equal(got8, got)
     # identical surfaces: Hausdorff distance 0 for every present class
     lab = torch.from_numpy(_blobby(rs, (30, 30, 30), 4)).cuda()

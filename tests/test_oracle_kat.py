@@ -119,3 +119,47 @@ def test_eval_meters_mdice_is_the_mean_over_volumes_of_the_per_volume_class_mean
     means, mm = meter.class_means()
     want, want_m = odice.eval_meters(np.stack([odice.dice_from_counts(c) for c in counts]))
     assert np.allclose(means, want, equal_nan=True) and mm == pytest.approx(want_m) and np.isnan(means[3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Known answers of MONAI 0.8.1's OWN unit tests for the metrics the reference wires in (engine/test.py:28-31), RECALLED
+# from memory of tests/test_compute_meandice.py and tests/test_hausdorff_distance.py - unverifiable offline (MONAI is not
+# installable here).  Each is also a geometric / arithmetic truth, so a wrong recollection could not make them pass.
+# (The erf taps of GaussianFilter have no such pin: the expected array remembered from tests/test_gaussian_filter.py
+# reproduces to 4e-8 with the pre-0.4 kernel exp(-x^2/2s^2)/sum, i.e. it predates the erf formula of 0.8 - not used.)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_monai_compute_meandice_case_1_and_nan_case():
+    # TEST_CASE_1: y_pred [[[[1, 0], [0, 1]]]], y [[[[1, 0], [1, 1]]]], include_background=True -> [[0.8]]
+    pred = np.array([[1, 0], [0, 1]], dtype=np.uint8)
+    y = np.array([[1, 0], [1, 1]], dtype=np.uint8)
+    c = odice.dice_counts(pred, y, 2)
+    assert odice.dice_from_counts(c)[1] == pytest.approx(0.8)          # 2 * 2 / (3 + 2)
+    logits = torch.stack([torch.from_numpy(1.0 - pred), torch.from_numpy(pred * 1.0)]).reshape(2, 1, 2, 2).float()
+    md = odice.monai_meandice(logits, torch.from_numpy(y).reshape(1, 1, 2, 2).float(), 2)
+    assert md[0, 1].item() == pytest.approx(0.8)
+    # TEST_NAN_CASE: an all-zero ground truth channel -> NaN
+    empty = odice.dice_counts(pred, np.zeros_like(y), 2)
+    assert np.isnan(odice.dice_from_counts(empty)[1])
+
+
+def _spherical_seg_3d(radius=20.0, centre=(49, 49, 49), value=1, im_shape=(99, 99, 99)):
+    """tests/test_hausdorff_distance.py::create_spherical_seg_3d"""
+    image = np.zeros(im_shape, dtype=np.int32)
+    spy, spx, spz = np.ogrid[-centre[0]:im_shape[0] - centre[0], -centre[1]:im_shape[1] - centre[1],
+                             -centre[2]:im_shape[2] - centre[2]]
+    image[(spx * spx + spy * spy + spz * spz) <= radius * radius] = value
+    return image
+
+
+def test_monai_hausdorff_sphere_cases():
+    from oracle import hausdorff as ohd
+    same = ohd.hausdorff_distance(_spherical_seg_3d(), _spherical_seg_3d(), 2, percentile=None)
+    assert same[1] == 0.0
+    a = _spherical_seg_3d(radius=20, centre=(20, 20, 20))
+    b = _spherical_seg_3d(radius=20, centre=(19, 19, 19))
+    assert ohd.hausdorff_distance(a, b, 2, percentile=None)[1] == pytest.approx(1.7320508075688772)   # sqrt(3)
+    a = _spherical_seg_3d(radius=33, value=2, centre=(19, 33, 22))
+    b = _spherical_seg_3d(radius=33, value=2, centre=(20, 33, 22))
+    assert ohd.hausdorff_distance(a, b, 3, percentile=None)[2] == 1.0
+    assert ohd.hausdorff_distance(a, b, 3, percentile=95)[2] == 1.0
