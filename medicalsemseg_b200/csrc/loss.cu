@@ -30,20 +30,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_constant__ LossParams p) {
+// E voxels per thread (2: 8-byte loads, ~80 registers, 6 CTAs/SM; the first version took 4 with 150 registers and three
+// CTAs/SM and ran at 0.29 of the HBM roofline).  The sums that only the labelled class receives (I, G) live in a private
+// shared-memory column per thread ([class][thread]: conflict-free, no atomics); P stays in registers.
+constexpr int kLossE = 2;
+
+__global__ void __launch_bounds__(kLossThreads, 6) dice_ce_kernel(const __grid_constant__ LossParams p) {
     __shared__ double sh[3 * kLossMaxK + 1];
+    __shared__ float sI[kLossMaxK][kLossThreads], sG[kLossMaxK][kLossThreads];
     for (int i = threadIdx.x; i < 3 * kLossMaxK + 1; i += kLossThreads) sh[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < kLossMaxK; ++c) sI[c][threadIdx.x] = 0.f, sG[c][threadIdx.x] = 0.f;
     __syncthreads();
     const int K = p.K;
-    const int nq = (p.row_len + 3) / 4;
+    const int nq = (p.row_len + kLossE - 1) / kLossE;
     const long long total = p.n_rows * nq;
-    const bool vec = (p.row_len % 4 == 0) && (p.row_pitch % 4 == 0) && (p.class_stride % 4 == 0) &&
-                     (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0);
+    const bool vec = (p.row_len % kLossE == 0) && (p.row_pitch % kLossE == 0) && (p.class_stride % kLossE == 0) &&
+                     (reinterpret_cast<uintptr_t>(p.logits) % (4 * kLossE) == 0);
     const int lane = threadIdx.x & 31;
-    // per-thread partial sums over the thread's quads (a few hundred float additions), reduced once at the end
-    float aI[kLossMaxK], aP[kLossMaxK], aG[kLossMaxK], ce = 0.f;
+    float aP[kLossMaxK], ce = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLossMaxK; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+    for (int c = 0; c < kLossMaxK; ++c) aP[c] = 0.f;
     auto flush = [&]() {  // warp sums -> float64 in shared memory; every lane of the warp takes part
         ce = warp_sum(ce);
         if (lane == 0 && ce != 0.f) atomicAdd(&sh[3 * kLossMaxK], static_cast<double>(ce));
@@ -51,13 +58,15 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < kLossMaxK; ++c) {
             if (c < K) {
-                const float inter = warp_sum(aI[c]), psq = warp_sum(aP[c]), g = warp_sum(aG[c]);
+                const float inter = warp_sum(sI[c][threadIdx.x]), psq = warp_sum(aP[c]), g = warp_sum(sG[c][threadIdx.x]);
                 if (lane == 0) {
                     if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
                     if (psq != 0.f) atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
                     if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
                 }
-                aI[c] = aP[c] = aG[c] = 0.f;
+                aP[c] = 0.f;
+                sI[c][threadIdx.x] = 0.f;
+                sG[c][threadIdx.x] = 0.f;
             }
         }
     };
@@ -65,29 +74,30 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
     // the trip count is per warp (lanes past the end idle), so the periodic flush can use full-warp shuffles
     for (long long i0 = static_cast<long long>(blockIdx.x) * kLossThreads + (threadIdx.x & ~31); i0 < total;
          i0 += static_cast<long long>(gridDim.x) * kLossThreads) {
-        if ((++iters & 63) == 0) flush();  // at most 256 float additions per accumulator between float64 hand-overs
+        if ((++iters & 127) == 0) flush();  // at most 256 float additions per accumulator between float64 hand-overs
         const long long i = i0 + lane;
         if (i >= total) continue;
         const long long row = i / nq;
-        const int x0 = static_cast<int>(i - row * nq) * 4;
-        const int nv = min(4, p.row_len - x0);
-        float v[kLossMaxK][4];
+        const int x0 = static_cast<int>(i - row * nq) * kLossE;
+        const int nv = min(kLossE, p.row_len - x0);
+        float v[kLossMaxK][kLossE];
         const float* src = p.logits + row * p.row_pitch + x0;
 #pragma unroll
         for (int c = 0; c < kLossMaxK; ++c) {
             if (c < K) {
                 if (vec) {
-                    const float4 f = ld_stream_f4(src + c * p.class_stride);
-                    v[c][0] = f.x, v[c][1] = f.y, v[c][2] = f.z, v[c][3] = f.w;
+                    float2 f;
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(f.x), "=f"(f.y) : "l"(src + c * p.class_stride));
+                    v[c][0] = f.x, v[c][1] = f.y;
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[c][e] = e < nv ? __ldg(src + c * p.class_stride + e) : 0.f;
+                    for (int e = 0; e < kLossE; ++e) v[c][e] = e < nv ? __ldg(src + c * p.class_stride + e) : 0.f;
                 }
             }
         }
-        int y[4];
+        int y[kLossE];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < kLossE; ++e) {
             y[e] = -1;
             if (e < nv) {
                 const long long li = row * p.row_len + x0 + e;
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
         }
         // softmax per voxel (max-subtracted, like torch), log-softmax of the labelled class for the cross-entropy
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < kLossE; ++e) {
             if (e >= nv) continue;
             float m = -INFINITY;
 #pragma unroll
@@ -117,13 +127,13 @@ __global__ void __launch_bounds__(kLossThreads, 3) dice_ce_kernel(const __grid_c
                 if (c < K) {
                     const float pc = v[c][e] * inv;
                     aP[c] += p.squared ? pc * pc : pc;
-                    if (c == y[e]) {
-                        py = pc;
-                        aI[c] += pc;
-                        aG[c] += 1.f;
-                    }
+                    py = c == y[e] ? pc : py;
                 }
-            if (y[e] >= 0 && y[e] < K) ce -= __logf(py);
+            if (y[e] >= 0 && y[e] < K) {
+                ce -= __logf(py);
+                sI[y[e]][threadIdx.x] += py;
+                sG[y[e]][threadIdx.x] += 1.f;
+            }
         }
     }
     flush();
@@ -159,9 +169,9 @@ extern "C" int mss_dice_ce_sums(const float* logits, int64_t class_stride, int64
     p.K = n_classes;
     p.squared = squared_pred != 0;
     p.sums = sums;
-    const long long work = n_rows * ((row_len + 3) / 4);
+    const long long work = n_rows * ((row_len + kLossE - 1) / kLossE);
     long long blocks = (work + kLossThreads - 1) / kLossThreads;
-    if (blocks > 148LL * 3) blocks = 148LL * 3;  // one resident wave: the per-thread partial sums are reduced once per thread
+    if (blocks > 148LL * 6) blocks = 148LL * 6;  // one resident wave: the per-thread partial sums are reduced once per thread
     dice_ce_kernel<<<static_cast<unsigned>(blocks), kLossThreads, 0, as_stream(stream)>>>(p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
