@@ -453,3 +453,21 @@ def test_dice_counts_batched_equals_per_volume(ldt, n):
     for i in range(b):
         single.update(torch.from_numpy(pred[i]).cuda(), lab_t[i])
     assert np.allclose(meter.class_means()[0], single.class_means()[0], equal_nan=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """The dynamic shared-memory opt-in of the accumulate / extract / resample kernels is per device: stitching on cuda:0
+    and then on cuda:1 from the same process must work (round-1 advisor finding: a process-wide `static bool`)."""
+    from oracle import sliding_window as osw
+    from oracle.predictors import ArithmeticPredictor
+    rs = np.random.RandomState(3)
+    vol = torch.from_numpy(rs.standard_normal((1, 1, 40, 36, 44)).astype(np.float32))
+    pred = ArithmeticPredictor(5)
+    ref = osw.sliding_window_inference(vol, None, (16, 16, 16), 4, pred, overlap=0.5, mode="gaussian", tuple_input=False)
+    for dev in ("cuda:0", "cuda:1"):
+        out = mss.sliding_window_inference(vol.to(dev), None, (16, 16, 16), 4, pred, overlap=0.5, mode="gaussian",
+                                           mss_tuple_input=False)
+        assert out.device == torch.device(dev) and torch.equal(out.cpu(), ref)
+        lab = mss.resample_3d(mss.sliding_window_infer(vol.to(dev), pred, (16, 16, 16), 0.5, "gaussian")[0], (50, 30, 61))
+        assert lab.device == torch.device(dev)
