@@ -38,10 +38,17 @@ __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__
             const uint8_t* row = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + p.lo[2];
             const long long o = (static_cast<long long>(z) * p.n[1] + y) * p.n[2];
             const int x1 = min(x0 + kEdgeRun, p.n[2]);
+            unsigned long long packed = 0ull;  // the run's 8 edge bytes, stored with one 8-byte store where aligned
             for (int x = x0; x < x1; ++x) {
                 const bool edge = mask_edge_at(row + x, sz, sy, z, y, x, p.n, cls);
-                p.edges[o + x] = edge ? 1 : 0;
+                packed |= static_cast<unsigned long long>(edge ? 1u : 0u) << (8 * (x - x0));
                 if (p.h != nullptr) p.h[o + x] = edge ? 0 : kEdtInf;
+            }
+            uint8_t* dst = p.edges + o + x0;
+            if (x1 - x0 == kEdgeRun && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
+                *reinterpret_cast<unsigned long long*>(dst) = packed;
+            } else {
+                for (int x = x0; x < x1; ++x) dst[x - x0] = static_cast<uint8_t>(packed >> (8 * (x - x0)));
             }
         }
 }

@@ -58,10 +58,8 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const __grid_cons
     const unsigned pre0 = p.st->prefix[0], pre1 = p.st->prefix[1];
     const bool same = level == 0 || pre0 == pre1;  // both ranks still in the same bucket chain: one histogram serves both
     unsigned kmax = 0u;
-    for (long long i = static_cast<long long>(blockIdx.x) * kSelThreads + threadIdx.x; i < p.n_elems;
-         i += static_cast<long long>(gridDim.x) * kSelThreads) {
-        if (p.mask != nullptr && p.mask[i] == 0) continue;
-        const unsigned key = map_key(p.keys[i], p.key_kind);
+    auto handle = [&](unsigned raw) {
+        const unsigned key = map_key(raw, p.key_kind);
         const unsigned hi = level == 0 ? 0u : key >> (shift + bits);
         const unsigned b = (key >> shift) & bmask;
         if (level == 0) {
@@ -71,6 +69,35 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const __grid_cons
             if (hi == pre0) atomicAdd(&sh[0][b], 1u);
             if (!same && hi == pre1) atomicAdd(&sh[1][b], 1u);
         }
+    };
+    const long long tid = static_cast<long long>(blockIdx.x) * kSelThreads + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * kSelThreads;
+    // 16 elements per step: one 16-byte load of the mask (most of a surface mask is zero: skipped without touching the keys)
+    // or, unmasked, four 16-byte loads of keys
+    const bool vec = reinterpret_cast<uintptr_t>(p.keys) % 16 == 0 && (p.mask == nullptr || reinterpret_cast<uintptr_t>(p.mask) % 16 == 0);
+    const long long n16 = vec ? p.n_elems / 16 : 0;
+    for (long long i = tid; i < n16; i += stride) {
+        if (p.mask != nullptr) {
+            const uint4 m = ld_stream_u4(p.mask + i * 16);
+            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (mw[w] == 0u) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((mw[w] >> (8 * e)) & 0xffu) handle(p.keys[i * 16 + 4 * w + e]);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint4 k4 = ld_stream_u4(p.keys + i * 16 + 4 * w);
+                handle(k4.x), handle(k4.y), handle(k4.z), handle(k4.w);
+            }
+        }
+    }
+    for (long long i = n16 * 16 + tid; i < p.n_elems; i += stride) {
+        if (p.mask != nullptr && p.mask[i] == 0) continue;
+        handle(p.keys[i]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) {
