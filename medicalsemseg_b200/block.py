@@ -1,4 +1,5 @@
-"""Block (up to 3-D) partition of ONE large volume over the GPUs of a box: the general form of slab.py.
+"""Block (up to 3-D) partition of ONE large volume over the GPUs of a box; 1-D slabs (slab.py) are the special case of one
+cut axis and share every line of this file.
 
 The 1-D slab split of BASELINE.json configs[2] (21 window starts along the long axis over 8 ranks = 3/3/3/3/3/2/2/2)
 caps the speed-up at 2100 / 300 = 7.0x because window starts only come in whole layers of 100 windows.  Cutting the
@@ -6,7 +7,7 @@ window-index box along several axes balances better: 2 x 2 x 2 blocks of the 10 
 5 * 5 * 11 = 275 windows (7.64x), 1 x 2 x 2 blocks on 4 ranks 550 instead of 600.  ``choose_dims`` picks the
 factorisation of the world size with the smallest maximum window count (ties: fewer cut axes, i.e. less halo).
 
-Per axis everything is the 1-D logic of slab.py (``SlabPartition``: window-start ranges, buffer box, owned planes,
+Per axis everything is 1-D (``SlabPartition``: window-start ranges, buffer box, owned planes,
 halo = planes written beyond the ownership).  Halos are reduced one axis after the other - W, then H, then D: a rank
 ships the planes beyond its ownership along the axis over the FULL extent of its buffer in the axes not yet reduced
 (and only its owned range in the axes already done) to its +1 neighbour along that axis, which adds them
@@ -22,8 +23,88 @@ import torch
 
 from . import _lib
 from .grid import WindowGrid, make_grid
-from .slab import SlabPartition, cuda_halo_add, partition
 
+
+# ---- one axis: contiguous ranges of window starts (the 1-D "z-slab" split of BASELINE.json configs[2]) -------------------
+
+@dataclass
+class SlabPartition:
+    axis: int
+    world: int
+    win_lo: List[int]   # first window-start index of each rank along `axis`
+    win_hi: List[int]   # one past the last
+    buf_lo: List[int]   # global coordinate where each rank's buffer begins
+    buf_hi: List[int]
+    own_lo: List[int]   # planes each rank finalises
+    own_hi: List[int]
+
+    def halo(self, rank: int) -> Tuple[int, int]:
+        """Global plane range rank `rank` wrote but does not own (empty for the last rank)."""
+        return (self.own_hi[rank], self.buf_hi[rank]) if rank + 1 < self.world else (0, 0)
+
+    def halo_depends_on_previous(self, rank: int) -> bool:
+        """Does rank-1's halo reach into the planes `rank` itself has to forward?"""
+        if rank == 0 or rank + 1 >= self.world:
+            return False
+        return self.halo(rank - 1)[1] > self.own_hi[rank]
+
+
+def split_counts(n: int, world: int) -> List[int]:
+    """n window starts over `world` ranks, larger shares first (21 over 8 -> 3,3,3,3,3,2,2,2)."""
+    base, extra = divmod(n, world)
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def partition(grid: WindowGrid, world: int, axis: Optional[int] = None) -> SlabPartition:
+    ns = grid.n_starts
+    if axis is None:
+        axis = max(range(3), key=lambda a: ns[a])
+    if ns[axis] < world:
+        raise ValueError(f"axis {axis} has {ns[axis]} window starts: cannot partition over {world} ranks")
+    counts = split_counts(ns[axis], world)
+    lo, hi, acc = [], [], 0
+    for c in counts:
+        lo.append(acc)
+        acc += c
+        hi.append(acc)
+    st = grid.starts[axis]
+    roi = grid.roi[axis]
+    buf_lo = [st[l] for l in lo]
+    buf_hi = [st[h - 1] + roi for h in hi]
+    own_lo = [0] + [st[l] for l in lo[1:]]
+    own_hi = own_lo[1:] + [grid.image_size[axis]]
+    return SlabPartition(axis, world, lo, hi, buf_lo, buf_hi, own_lo, own_hi)
+
+
+def _region(t: torch.Tensor, axis: int, lo: int, hi: int) -> torch.Tensor:
+    """View of planes [lo, hi) (buffer-local) along spatial `axis` of a [Nb, K, D, H, W] tensor."""
+    idx = [slice(None)] * 5
+    idx[2 + axis] = slice(lo, hi)
+    return t[tuple(idx)]
+
+
+def cuda_halo_add(dst_view: torch.Tensor, src: torch.Tensor) -> None:
+    """``dst_view += src`` with the library kernel, one launch.  Both are (strided) views of up to 5 dimensions whose
+    innermost dimension is contiguous - a box of an accumulator; ``src`` may be a peer GPU's memory."""
+    if dst_view.shape != src.shape:
+        raise ValueError(f"halo shapes differ: {tuple(dst_view.shape)} vs {tuple(src.shape)}")
+    if dst_view.dim() > 5 or dst_view.dim() < 1:
+        raise ValueError("halo boxes have 1..5 dimensions")
+    if dst_view.numel() == 0:
+        return
+    if dst_view.stride(-1) != 1 or src.stride(-1) != 1:
+        raise ValueError("the innermost halo dimension must be contiguous")
+    outer = dst_view.dim() - 1
+    dims = [1] * (4 - outer) + list(dst_view.shape[:-1])
+    dst_s = [0] * (4 - outer) + list(dst_view.stride()[:-1])
+    src_s = [0] * (4 - outer) + list(src.stride()[:-1])
+    I4 = _lib.c_i64 * 4
+    rc = _lib.load().mss_halo_add_nd(dst_view.data_ptr(), I4(*dst_s), src.data_ptr(), I4(*src_s), I4(*dims),
+                                     dst_view.shape[-1], torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mss_halo_add_nd")
+
+
+# ---- blocks ---------------------------------------------------------------------------------------------------------------
 
 @dataclass
 class BlockPartition:
