@@ -67,16 +67,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// L2 policies: the volume is read by up to 8 overlapping windows and should stay in the 126 MB L2 (evict_last); the patches
+// are written once and read much later by the backbone (evict_first), so 1 GB of stores does not flush the volume out
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
+                                            int c3, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3,
+                                             uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -112,15 +125,18 @@ __device__ __forceinline__ TileCoord tile_coord(const ExtractParams& p, long lon
     return tc;
 }
 
+constexpr int kCoordRing = 64;  // tile coordinates computed ahead by the whole warp
+
 __global__ void __launch_bounds__(32) extract_tma_kernel(const __grid_constant__ CUtensorMap in_map,
                                                          const __grid_constant__ CUtensorMap out_map,
                                                          const ExtractParams p, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[kTmaStages];
+    __shared__ TileCoord s_tc[kCoordRing];
+    const int lane = threadIdx.x;
 
     if (blockIdx.x == 0 && p.centers != nullptr)
-        for (int w = threadIdx.x; w < p.n_windows; w += 32) write_centers(p, w);
-    if (threadIdx.x != 0) return;
+        for (int w = lane; w < p.n_windows; w += 32) write_centers(p, w);
 
     const int tiles_h = (p.g.roi[1] + kTmaBoxH - 1) / kTmaBoxH;
     const int tiles_d = (p.g.roi[0] + kTmaBoxD - 1) / kTmaBoxD;
@@ -129,39 +145,60 @@ __global__ void __launch_bounds__(32) extract_tma_kernel(const __grid_constant__
     const long long mine = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (mine == 0) return;
 
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) {
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // Where a tile comes from and goes to (window decode: divisions and three dependent loads of window starts) is worked
+    // out by ALL 32 lanes, 32 tiles at a time, one batch ahead of the elected lane that drives the copies - the first
+    // version did it in the elected lane, twice per tile, and spent ~1.8 us per 12 KB tile there (0.70 of the roofline).
+    auto fill = [&](long long first) {  // coordinates of tiles [first, first + 32) of this CTA into the ring
+        const long long i = first + lane;
+        if (i < mine) s_tc[i % kCoordRing] = tile_coord(p, blockIdx.x + i * gridDim.x, tiles_h, tiles_d);
+    };
+    fill(0);
+    fill(32);
+    __syncwarp();
 
     // the rows a box pulls that lie beyond roi_h / roi_d are never stored (the store clips at the patch
     // tensor's extent), so the byte count of every load is the full box
     const uint32_t tx = static_cast<uint32_t>(stage_bytes);
-
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     auto issue_load = [&](long long i) {
         const int s = static_cast<int>(i % kTmaStages);
-        const TileCoord tc = tile_coord(p, blockIdx.x + i * gridDim.x, tiles_h, tiles_d);
+        const TileCoord tc = s_tc[i % kCoordRing];
         mbar_expect_tx(&full[s], tx);
         tma_load_4d(smem + static_cast<size_t>(s) * stage_bytes, &in_map, &full[s], tc.in_c[0], tc.in_c[1], tc.in_c[2],
-                    tc.in_c[3]);
+                    tc.in_c[3], pol_keep);
     };
 
-    const long long prologue = mine < kTmaStages ? mine : kTmaStages;
-    for (long long i = 0; i < prologue; ++i) issue_load(i);
-
-    for (long long i = 0; i < mine; ++i) {
-        const int s = static_cast<int>(i % kTmaStages);
-        mbar_wait(&full[s], static_cast<uint32_t>((i / kTmaStages) & 1));
-        const TileCoord tc = tile_coord(p, blockIdx.x + i * gridDim.x, tiles_h, tiles_d);
-        tma_store_4d(&out_map, smem + static_cast<size_t>(s) * stage_bytes, tc.out_c[0], tc.out_c[1], tc.out_c[2],
-                     tc.out_c[3]);
-        tma_store_commit();
-        // refill the stage whose store was issued one iteration ago: allow only the newest store to be pending
-        if (i >= 1 && i - 1 + kTmaStages < mine) {
-            tma_store_wait_read<1>();
-            issue_load(i - 1 + kTmaStages);
-        }
+    if (lane == 0) {
+        const long long prologue = mine < kTmaStages ? mine : kTmaStages;
+        for (long long i = 0; i < prologue; ++i) issue_load(i);
     }
-    tma_store_wait_read<0>();  // smem must outlive the last bulk reads
+    for (long long base = 0; base < mine; base += 32) {
+        if (lane == 0) {
+            const long long end = base + 32 < mine ? base + 32 : mine;
+            for (long long i = base; i < end; ++i) {
+                const int s = static_cast<int>(i % kTmaStages);
+                mbar_wait(&full[s], static_cast<uint32_t>((i / kTmaStages) & 1));
+                const TileCoord tc = s_tc[i % kCoordRing];
+                tma_store_4d(&out_map, smem + static_cast<size_t>(s) * stage_bytes, tc.out_c[0], tc.out_c[1], tc.out_c[2],
+                             tc.out_c[3], pol_stream);
+                tma_store_commit();
+                // refill the stage whose store was issued one iteration ago: allow only the newest store to be pending
+                if (i >= 1 && i - 1 + kTmaStages < mine) {
+                    tma_store_wait_read<1>();
+                    issue_load(i - 1 + kTmaStages);  // <= base + 30 + kTmaStages < base + 64: inside the ring
+                }
+            }
+        }
+        __syncwarp();
+        fill(base + kCoordRing);  // overwrites the batch just finished
+        __syncwarp();
+    }
+    if (lane == 0) tma_store_wait_read<0>();  // smem must outlive the last bulk reads
 }
 
 // ---- fallback path ------------------------------------------------------------------------------
