@@ -35,39 +35,39 @@ __device__ __forceinline__ float warp_sum(float v) {
 // shared-memory column per thread ([class][thread]: conflict-free, no atomics); P stays in registers.
 constexpr int kLossE = 2;
 
+// K is a template parameter: with a run-time class count the 16-wide unrolled loops carried a compare and a branch per
+// class and stage (970 warp instructions per 2 voxels, 64 % issue-active: instruction-bound at 0.41 of the roofline).
+template <int K>
 __global__ void __launch_bounds__(kLossThreads, 6) dice_ce_kernel(const __grid_constant__ LossParams p) {
     __shared__ double sh[3 * kLossMaxK + 1];
-    __shared__ float sI[kLossMaxK][kLossThreads], sG[kLossMaxK][kLossThreads];
+    __shared__ float sI[K][kLossThreads], sG[K][kLossThreads];
     for (int i = threadIdx.x; i < 3 * kLossMaxK + 1; i += kLossThreads) sh[i] = 0.0;
 #pragma unroll
-    for (int c = 0; c < kLossMaxK; ++c) sI[c][threadIdx.x] = 0.f, sG[c][threadIdx.x] = 0.f;
+    for (int c = 0; c < K; ++c) sI[c][threadIdx.x] = 0.f, sG[c][threadIdx.x] = 0.f;
     __syncthreads();
-    const int K = p.K;
     const int nq = (p.row_len + kLossE - 1) / kLossE;
     const long long total = p.n_rows * nq;
     const bool vec = (p.row_len % kLossE == 0) && (p.row_pitch % kLossE == 0) && (p.class_stride % kLossE == 0) &&
                      (reinterpret_cast<uintptr_t>(p.logits) % (4 * kLossE) == 0);
     const int lane = threadIdx.x & 31;
-    float aP[kLossMaxK], ce = 0.f;
+    float aP[K], ce = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLossMaxK; ++c) aP[c] = 0.f;
+    for (int c = 0; c < K; ++c) aP[c] = 0.f;
     auto flush = [&]() {  // warp sums -> float64 in shared memory; every lane of the warp takes part
         ce = warp_sum(ce);
         if (lane == 0 && ce != 0.f) atomicAdd(&sh[3 * kLossMaxK], static_cast<double>(ce));
         ce = 0.f;
 #pragma unroll
-        for (int c = 0; c < kLossMaxK; ++c) {
-            if (c < K) {
-                const float inter = warp_sum(sI[c][threadIdx.x]), psq = warp_sum(aP[c]), g = warp_sum(sG[c][threadIdx.x]);
-                if (lane == 0) {
-                    if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
-                    if (psq != 0.f) atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
-                    if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
-                }
-                aP[c] = 0.f;
-                sI[c][threadIdx.x] = 0.f;
-                sG[c][threadIdx.x] = 0.f;
+        for (int c = 0; c < K; ++c) {
+            const float inter = warp_sum(sI[c][threadIdx.x]), psq = warp_sum(aP[c]), g = warp_sum(sG[c][threadIdx.x]);
+            if (lane == 0) {
+                if (inter != 0.f) atomicAdd(&sh[c], static_cast<double>(inter));
+                if (psq != 0.f) atomicAdd(&sh[kLossMaxK + c], static_cast<double>(psq));
+                if (g != 0.f) atomicAdd(&sh[2 * kLossMaxK + c], static_cast<double>(g));
             }
+            aP[c] = 0.f;
+            sI[c][threadIdx.x] = 0.f;
+            sG[c][threadIdx.x] = 0.f;
         }
     };
     int iters = 0;
@@ -80,19 +80,17 @@ __global__ void __launch_bounds__(kLossThreads, 6) dice_ce_kernel(const __grid_c
         const long long row = i / nq;
         const int x0 = static_cast<int>(i - row * nq) * kLossE;
         const int nv = min(kLossE, p.row_len - x0);
-        float v[kLossMaxK][kLossE];
+        float v[K][kLossE];
         const float* src = p.logits + row * p.row_pitch + x0;
 #pragma unroll
-        for (int c = 0; c < kLossMaxK; ++c) {
-            if (c < K) {
-                if (vec) {
-                    float2 f;
-                    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(f.x), "=f"(f.y) : "l"(src + c * p.class_stride));
-                    v[c][0] = f.x, v[c][1] = f.y;
-                } else {
+        for (int c = 0; c < K; ++c) {
+            if (vec) {
+                float2 f;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(f.x), "=f"(f.y) : "l"(src + c * p.class_stride));
+                v[c][0] = f.x, v[c][1] = f.y;
+            } else {
 #pragma unroll
-                    for (int e = 0; e < kLossE; ++e) v[c][e] = e < nv ? __ldg(src + c * p.class_stride + e) : 0.f;
-                }
+                for (int e = 0; e < kLossE; ++e) v[c][e] = e < nv ? __ldg(src + c * p.class_stride + e) : 0.f;
             }
         }
         int y[kLossE];
@@ -111,24 +109,21 @@ __global__ void __launch_bounds__(kLossThreads, 6) dice_ce_kernel(const __grid_c
             if (e >= nv) continue;
             float m = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < kLossMaxK; ++c)
-                if (c < K) m = fmaxf(m, v[c][e]);
+            for (int c = 0; c < K; ++c) m = fmaxf(m, v[c][e]);
             float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < kLossMaxK; ++c)
-                if (c < K) {
-                    v[c][e] = __expf(v[c][e] - m);  // ex2.approx path: ~2 ulp, far inside the 1e-5 bar of a 50 M-term mean
-                    s += v[c][e];
-                }
+            for (int c = 0; c < K; ++c) {
+                v[c][e] = __expf(v[c][e] - m);  // ex2.approx path: ~2 ulp, far inside the 1e-5 bar of a 50 M-term mean
+                s += v[c][e];
+            }
             const float inv = __fdividef(1.f, s);
             float py = 1.f;
 #pragma unroll
-            for (int c = 0; c < kLossMaxK; ++c)
-                if (c < K) {
-                    const float pc = v[c][e] * inv;
-                    aP[c] += p.squared ? pc * pc : pc;
-                    py = c == y[e] ? pc : py;
-                }
+            for (int c = 0; c < K; ++c) {
+                const float pc = v[c][e] * inv;
+                aP[c] += p.squared ? pc * pc : pc;
+                py = c == y[e] ? pc : py;
+            }
             if (y[e] >= 0 && y[e] < K) {
                 ce -= __logf(py);
                 sI[y[e]][threadIdx.x] += py;
@@ -172,7 +167,15 @@ extern "C" int mss_dice_ce_sums(const float* logits, int64_t class_stride, int64
     const long long work = n_rows * ((row_len + kLossE - 1) / kLossE);
     long long blocks = (work + kLossThreads - 1) / kLossThreads;
     if (blocks > 148LL * 6) blocks = 148LL * 6;  // one resident wave: the per-thread partial sums are reduced once per thread
-    dice_ce_kernel<<<static_cast<unsigned>(blocks), kLossThreads, 0, as_stream(stream)>>>(p);
+    const unsigned nb = static_cast<unsigned>(blocks);
+    cudaStream_t st = as_stream(stream);
+    switch (n_classes) {
+#define MSS_LOSS_CASE(KK) case KK: dice_ce_kernel<KK><<<nb, kLossThreads, 0, st>>>(p); break;
+        MSS_LOSS_CASE(1) MSS_LOSS_CASE(2) MSS_LOSS_CASE(3) MSS_LOSS_CASE(4) MSS_LOSS_CASE(5) MSS_LOSS_CASE(6) MSS_LOSS_CASE(7)
+        MSS_LOSS_CASE(8) MSS_LOSS_CASE(9) MSS_LOSS_CASE(10) MSS_LOSS_CASE(11) MSS_LOSS_CASE(12) MSS_LOSS_CASE(13)
+        MSS_LOSS_CASE(14) MSS_LOSS_CASE(15) MSS_LOSS_CASE(16)
+#undef MSS_LOSS_CASE
+    }
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }
