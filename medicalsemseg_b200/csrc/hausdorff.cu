@@ -23,30 +23,101 @@ struct EdgeParams {
     int* h;
 };
 
-// grid: x over the (y, x-chunk) pairs of one plane of the box, y over its planes; a thread walks kEdgeRun voxels of a
-// row with one set of row pointers
+// grid: x over the (y, x-chunk) pairs of one plane of the box, y over its planes.  A thread decides kEdgeRun = 8 voxels
+// of a row at once on packed bytes: the five rows it needs (centre, +-1 row, +-1 plane) come in as aligned 32-bit words
+// funnel-shifted to the run's first byte, `byte == class` is one SIMD compare per word, the W neighbours are the centre
+// row's words shifted by one byte, and a run without a single voxel of the class (most runs of an organ's box) stops
+// after the centre row.  ~60 instructions per 8 voxels where the voxel-by-voxel form (mask_edge_at, kept for the first
+// and last bytes of the volume and as the host-checked definition) spent ~25 per voxel.
 constexpr int kEdgeRun = 8;
+
+// bytes [0, 8) at `ptr` (any alignment) as two little-endian words, from aligned word loads
+__device__ __forceinline__ uint2 load_run8(const uint8_t* ptr) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+    const unsigned* w = reinterpret_cast<const unsigned*>(a & ~static_cast<uintptr_t>(3));
+    const unsigned sh = static_cast<unsigned>(a & 3u) * 8u;
+    const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = sh ? __ldg(w + 2) : 0u;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
 
 __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__ EdgeParams p) {
     const long long sy = p.dims[2], sz = static_cast<long long>(p.dims[1]) * p.dims[2];
     const int chunks = (p.n[2] + kEdgeRun - 1) / kEdgeRun;
     const int work = p.n[1] * chunks;
     const unsigned cls = static_cast<unsigned>(p.cls);
+    const unsigned cls4 = cls * 0x01010101u;
+    const uint8_t* vol_end = p.labels + static_cast<long long>(p.dims[0]) * sz;
     for (int z = blockIdx.y; z < p.n[0]; z += gridDim.y)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < work; i += gridDim.x * blockDim.x) {
             const int y = i / chunks, x0 = (i - y * chunks) * kEdgeRun;
             const uint8_t* row = p.labels + (p.lo[0] + z) * sz + (p.lo[1] + y) * sy + p.lo[2];
             const long long o = (static_cast<long long>(z) * p.n[1] + y) * p.n[2];
             const int x1 = min(x0 + kEdgeRun, p.n[2]);
+            const uint8_t* c = row + x0;
             unsigned long long packed = 0ull;  // the run's 8 edge bytes, stored with one 8-byte store where aligned
-            for (int x = x0; x < x1; ++x) {
-                const bool edge = mask_edge_at(row + x, sz, sy, z, y, x, p.n, cls);
-                packed |= static_cast<unsigned long long>(edge ? 1u : 0u) << (8 * (x - x0));
-                if (p.h != nullptr) p.h[o + x] = edge ? 0 : kEdtInf;
+            // word loads reach up to 4 bytes before / 16 bytes after the run's first byte (of any of the five rows): only
+            // inside the volume
+            if (p.h == nullptr && c - sz - 4 >= p.labels && c + sz + 16 <= vol_end) {
+                // centre row, bytes [-1, 9): left neighbours, the run, right neighbours
+                const uintptr_t a = reinterpret_cast<uintptr_t>(c - 1);
+                const unsigned* w = reinterpret_cast<const unsigned*>(a & ~static_cast<uintptr_t>(3));
+                const unsigned sh = static_cast<unsigned>(a & 3u) * 8u;
+                const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = sh > 8u ? __ldg(w + 3) : 0u;
+                const unsigned lo = __funnelshift_r(w0, w1, sh), mid = __funnelshift_r(w1, w2, sh), hi = __funnelshift_r(w2, w3, sh);
+                // validity of the run's bytes (the last run of a row may be short)
+                const int nv = x1 - x0;
+                const unsigned v0 = nv >= 4 ? 0xFFFFFFFFu : (1u << (8 * nv)) - 1u;
+                const unsigned v1 = nv >= 8 ? 0xFFFFFFFFu : (nv > 4 ? (1u << (8 * (nv - 4))) - 1u : 0u);
+                const unsigned c0 = __vcmpeq4(__funnelshift_r(lo, mid, 8), cls4) & v0;
+                const unsigned c1 = __vcmpeq4(__funnelshift_r(mid, hi, 8), cls4) & v1;
+                if (c0 | c1) {
+                    unsigned in0 = 0xFFFFFFFFu, in1 = 0xFFFFFFFFu;  // bytes whose existing neighbours are all of the class
+                    if (p.n[2] > 1) {
+                        unsigned l0 = __vcmpeq4(lo, cls4), l1 = __vcmpeq4(mid, cls4);
+                        unsigned r0 = __vcmpeq4(__funnelshift_r(lo, mid, 16), cls4), r1 = __vcmpeq4(__funnelshift_r(mid, hi, 16), cls4);
+                        if (x0 == 0) l0 &= 0xFFFFFF00u;  // outside the box: background
+                        // the voxel at x = n - 1 has no right neighbour inside the box
+                        const int xl = p.n[2] - 1 - x0;
+                        if (xl < 4) r0 &= ~(0xFFu << (8 * xl));
+                        else if (xl < 8) r1 &= ~(0xFFu << (8 * (xl - 4)));
+                        in0 &= l0 & r0;
+                        in1 &= l1 & r1;
+                    }
+                    if (p.n[1] > 1) {
+                        if (y == 0 || y == p.n[1] - 1) {
+                            in0 = in1 = 0u;
+                        } else {
+                            const uint2 u = load_run8(c - sy), d = load_run8(c + sy);
+                            in0 &= __vcmpeq4(u.x, cls4) & __vcmpeq4(d.x, cls4);
+                            in1 &= __vcmpeq4(u.y, cls4) & __vcmpeq4(d.y, cls4);
+                        }
+                    }
+                    if (p.n[0] > 1) {
+                        if (z == 0 || z == p.n[0] - 1) {
+                            in0 = in1 = 0u;
+                        } else {
+                            const uint2 u = load_run8(c - sz), d = load_run8(c + sz);
+                            in0 &= __vcmpeq4(u.x, cls4) & __vcmpeq4(d.x, cls4);
+                            in1 &= __vcmpeq4(u.y, cls4) & __vcmpeq4(d.y, cls4);
+                        }
+                    }
+                    const unsigned e0 = c0 & ~in0 & 0x01010101u, e1 = c1 & ~in1 & 0x01010101u;
+                    packed = static_cast<unsigned long long>(e0) | (static_cast<unsigned long long>(e1) << 32);
+                }
+            } else {
+                for (int x = x0; x < x1; ++x) {
+                    const bool edge = mask_edge_at(row + x, sz, sy, z, y, x, p.n, cls);
+                    packed |= static_cast<unsigned long long>(edge ? 1u : 0u) << (8 * (x - x0));
+                    if (p.h != nullptr) p.h[o + x] = edge ? 0 : kEdtInf;
+                }
             }
             uint8_t* dst = p.edges + o + x0;
-            if (x1 - x0 == kEdgeRun && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
+            const unsigned al = static_cast<unsigned>(reinterpret_cast<uintptr_t>(dst)) & 7u;
+            if (x1 - x0 == kEdgeRun && al == 0) {
                 *reinterpret_cast<unsigned long long*>(dst) = packed;
+            } else if (x1 - x0 == kEdgeRun && (al & 3u) == 0) {
+                *reinterpret_cast<unsigned*>(dst) = static_cast<unsigned>(packed);
+                *reinterpret_cast<unsigned*>(dst + 4) = static_cast<unsigned>(packed >> 32);
             } else {
                 for (int x = x0; x < x1; ++x) dst[x - x0] = static_cast<uint8_t>(packed >> (8 * (x - x0)));
             }

@@ -14,6 +14,7 @@
 // stores them with one 16-byte store (funnel-shifted 4-byte stores where the output row is not 16-byte aligned).
 // Gather kernel: the general fallback (rows wider than 4096 voxels or too long for shared memory), byte loads via L1.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -203,6 +204,166 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
     }
 }
 
+// Stream kernel (the default).  The output is walked as ONE flat byte stream in chunks of CB bytes, so every store is an
+// aligned CB-byte vector whatever the row length (rows of 147 voxels start at every alignment).  A chunk's position in
+// its row repeats with period P = oz / gcd(CB, oz) chunks = RS = CB / gcd(CB, oz) rows: thread c of a period slot always
+// gets the chunk that starts at byte CB * c of a period, so its gather plan - the z source offsets of its CB bytes and
+// how many of them still belong to the chunk's first row - is fixed and lives in registers; per period it only needs
+// the source rows of (at most) two output rows, which it tracks incrementally.  No staging, no barriers: the byte loads
+// go through L1, where the source rows of neighbouring threads meet.
+struct StreamParams {
+    const uint8_t* in;
+    uint8_t* out;
+    const int* ix;
+    const int* iy;
+    const int* iz;
+    int in_dims[3];
+    int out_dims[3];
+    int n_rows;         // n_volumes * ox * oy
+    long long total;    // output bytes
+    int P, RS, NS;      // chunks and rows per period, period slots per CTA
+    int periods;        // ceil(n_rows / RS)
+    int per_block;      // periods per CTA (a multiple of NS)
+};
+
+// one output row's source: advanced by a fixed number of rows per step
+struct RowCursor {
+    int oy, ox, b;
+    int xrow;     // (b * in_x + sx) * in_y, with sx = 0 when the x index is scipy's constant
+    bool xvalid;
+    __device__ __forceinline__ void load_x(const StreamParams& p) {
+        const int sx = __ldg(p.ix + ox);
+        xvalid = sx >= 0;
+        xrow = (b * p.in_dims[0] + (sx < 0 ? 0 : sx)) * p.in_dims[1];
+    }
+    __device__ __forceinline__ void init(const StreamParams& p, int row) {
+        const int r2 = row / p.out_dims[1];
+        oy = row - r2 * p.out_dims[1];
+        b = r2 / p.out_dims[0];
+        ox = r2 - b * p.out_dims[0];
+        load_x(p);
+    }
+    __device__ __forceinline__ void advance(const StreamParams& p, int step) {
+        oy += step;
+        if (oy >= p.out_dims[1]) {
+            const int q = oy / p.out_dims[1];
+            oy -= q * p.out_dims[1];
+            ox += q;
+            if (ox >= p.out_dims[0]) {
+                const int q2 = ox / p.out_dims[0];
+                ox -= q2 * p.out_dims[0];
+                b += q2;
+            }
+            load_x(p);
+        }
+    }
+    // first voxel of the source row (the tensor's first row when the output row is scipy's constant), and whether it is real
+    __device__ __forceinline__ unsigned src(const StreamParams& p, bool in_range, bool* valid) const {
+        const int sy = __ldg(p.iy + oy);
+        *valid = in_range && xvalid && sy >= 0;
+        return *valid ? static_cast<unsigned>(xrow + sy) * static_cast<unsigned>(p.in_dims[2]) : 0u;  // input < 4 GB (host)
+    }
+};
+
+template <int CB>
+struct ChunkStore;
+template <>
+struct ChunkStore<16> {
+    static __device__ __forceinline__ void st(uint8_t* d, const unsigned* w) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <>
+struct ChunkStore<8> {
+    static __device__ __forceinline__ void st(uint8_t* d, const unsigned* w) { *reinterpret_cast<uint2*>(d) = make_uint2(w[0], w[1]); }
+};
+template <>
+struct ChunkStore<4> {
+    static __device__ __forceinline__ void st(uint8_t* d, const unsigned* w) { *reinterpret_cast<unsigned*>(d) = w[0]; }
+};
+
+template <int CB>
+__global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_constant__ StreamParams p) {
+    constexpr int NW = CB / 4;
+    const int tid = threadIdx.x;
+    const int sub = tid / p.P, c = tid - sub * p.P;
+    if (sub >= p.NS) return;
+    const int oz = p.out_dims[2];
+    const int ro = (c * CB) / oz, z0 = c * CB - ro * oz;
+    const int n_first = min(CB, oz - z0);  // bytes of the chunk that lie in its first row (oz >= CB: at most two rows)
+    // the fixed gather plan
+    unsigned off[CB], second[CB];  // z source offset; all ones when the byte belongs to the chunk's second row
+    unsigned keep0[NW], keep1[NW];  // byte masks of the real voxels of the first / second row
+    bool clean = true;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) keep0[q] = keep1[q] = 0u;
+#pragma unroll
+    for (int e = 0; e < CB; ++e) {
+        int z = z0 + e;
+        z = z >= oz ? z - oz : z;
+        const int i = __ldg(p.iz + z);
+        off[e] = i < 0 ? 0u : static_cast<unsigned>(i);
+        second[e] = e < n_first ? 0u : ~0u;
+        clean = clean && i >= 0;
+        const unsigned m = i >= 0 ? 0xFFu << (8 * (e & 3)) : 0u;
+        keep0[e >> 2] |= e < n_first ? m : 0u;
+        keep1[e >> 2] |= e < n_first ? 0u : m;
+    }
+    const int first = blockIdx.x * p.per_block;
+    const int end = min(p.periods, first + p.per_block);
+    int per = first + sub;
+    if (per >= end) return;
+    RowCursor r0, r1;
+    int row = per * p.RS + ro;  // (n_rows + RS < 2^31: checked by the host)
+    r0.init(p, row);
+    r1.init(p, row + 1);
+    const int step = p.NS * p.RS;
+    long long o = (static_cast<long long>(per) * p.P + c) * CB;
+    const long long o_step = static_cast<long long>(p.NS) * p.P * CB;
+    // software pipeline: the byte loads of the NEXT period are issued before this period's bytes are packed and stored,
+    // so a thread has two periods of loads in flight (the launch is latency-bound otherwise: one DRAM round trip per
+    // period and thread)
+    unsigned b[CB], bn[CB];
+    bool v0, v1, vn0 = false, vn1 = false;
+    auto fetch = [&](unsigned (&dst)[CB], bool* w0, bool* w1) {
+        const unsigned s0 = r0.src(p, row < p.n_rows, w0);
+        const unsigned d1 = r1.src(p, row + 1 < p.n_rows, w1) - s0;
+#pragma unroll
+        for (int e = 0; e < CB; ++e) dst[e] = __ldg(p.in + (s0 + off[e] + (d1 & second[e])));
+    };
+    fetch(b, &v0, &v1);
+    for (;;) {
+        const bool more = per + p.NS < end;
+        if (more) {
+            row += step;
+            r0.advance(p, step);
+            r1.advance(p, step);
+            fetch(bn, &vn0, &vn1);
+        }
+        unsigned w[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+            w[q] = __byte_perm(__byte_perm(b[4 * q], b[4 * q + 1], 0x0040), __byte_perm(b[4 * q + 2], b[4 * q + 3], 0x0040), 0x5410);
+        if (!(clean && v0 && v1)) {
+#pragma unroll
+            for (int q = 0; q < NW; ++q) w[q] &= (v0 ? keep0[q] : 0u) | (v1 ? keep1[q] : 0u);
+        }
+        if (o + CB <= p.total) {
+            ChunkStore<CB>::st(p.out + o, w);
+        } else {
+#pragma unroll
+            for (int e = 0; e < CB; ++e)
+                if (o + e < p.total) p.out[o + e] = static_cast<uint8_t>(w[e >> 2] >> (8 * (e & 3)));
+        }
+        if (!more) break;
+        per += p.NS;
+        o += o_step;
+        v0 = vn0, v1 = vn1;
+#pragma unroll
+        for (int e = 0; e < CB; ++e) b[e] = bn[e];
+    }
+}
+
 __global__ void __launch_bounds__(256) resample_gather_kernel(const __grid_constant__ ResampleParams p) {
     const int oz_chunks = (p.out_dims[2] + 15) / 16;
     const long long rows = p.n_volumes * p.out_dims[0] * p.out_dims[1];
@@ -276,6 +437,58 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
     cudaStream_t s = as_stream(stream);
     const long long n_rows = n_volumes * out_dims[0] * out_dims[1];
     MSS_REQUIRE(n_rows < (1LL << 31), MSS_E_UNSUPPORTED, "resample_nearest: too many output rows for one call");
+    // ---- stream kernel: aligned CB-byte chunks of the flat output, fixed gather plan per thread --------------------
+    static const int force_cb = getenv("MSS_RESAMPLE_CB") ? atoi(getenv("MSS_RESAMPLE_CB")) : -1;  // tuning knob; 0 = rows kernel
+    if (force_cb != 0 && (reinterpret_cast<uintptr_t>(labels_out) & 15u) == 0 &&
+        static_cast<long long>(n_volumes) * in_dims[0] * in_dims[1] * in_dims[2] < (1LL << 32)) {
+        const int cands[3] = {force_cb > 0 ? force_cb : 16, 8, 4};
+        for (int ci = 0; ci < 3; ++ci) {
+            const int cb = cands[ci];
+            if ((cb != 4 && cb != 8 && cb != 16) || out_dims[2] < cb) continue;
+            int g = cb, r = out_dims[2] % cb;
+            while (r) {
+                const int t = g % r;
+                g = r;
+                r = t;
+            }
+            StreamParams sp;
+            sp.P = out_dims[2] / g;
+            sp.RS = cb / g;
+            if (sp.P > 512) continue;
+            sp.NS = sp.P <= 256 ? 256 / sp.P : 1;
+            const int threads = (sp.NS * sp.P + 31) / 32 * 32;
+            sp.in = labels_in;
+            sp.out = labels_out;
+            sp.ix = index_x;
+            sp.iy = index_y;
+            sp.iz = index_z;
+            for (int a = 0; a < 3; ++a) sp.in_dims[a] = in_dims[a], sp.out_dims[a] = out_dims[a];
+            if (n_rows + sp.RS + 1 >= (1LL << 31)) continue;
+            sp.n_rows = static_cast<int>(n_rows);
+            sp.total = n_rows * out_dims[2];
+            sp.periods = static_cast<int>((n_rows + sp.RS - 1) / sp.RS);
+            // one wave: as many CTAs as are resident together (a second, partial wave would run at a fraction of the occupancy)
+            int resident = 0;
+            MSS_CUDA(cb == 16  ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, resample_stream_kernel<16>, threads, 0)
+                     : cb == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, resample_stream_kernel<8>, threads, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, resample_stream_kernel<4>, threads, 0));
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const long long want = static_cast<long long>(sms) * (resident < 1 ? 1 : resident);
+            const long long units = (sp.periods + sp.NS - 1) / sp.NS;  // loop iterations of all CTAs together
+            const long long per_cta = (units + want - 1) / want;
+            sp.per_block = static_cast<int>(per_cta) * sp.NS;
+            const unsigned blocks = static_cast<unsigned>((sp.periods + sp.per_block - 1) / sp.per_block);
+            if (cb == 16)
+                resample_stream_kernel<16><<<blocks, threads, 0, s>>>(sp);
+            else if (cb == 8)
+                resample_stream_kernel<8><<<blocks, threads, 0, s>>>(sp);
+            else
+                resample_stream_kernel<4><<<blocks, threads, 0, s>>>(sp);
+            MSS_CUDA(cudaGetLastError());
+            return MSS_OK;
+        }
+    }
     p.n_chunks = (out_dims[2] + 15) / 16;
     p.slot_pitch = (in_dims[2] + 15 + 12 + 15) / 16 * 16;  // row + alignment offset + the 3-word gather window
     constexpr int kMaxStage = 96 * 1024;

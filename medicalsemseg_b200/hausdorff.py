@@ -8,7 +8,9 @@ distance transform of each surface (three ``mss_edt_pass`` launches), the distan
 float64 sqrt and NumPy's linear-interpolation percentile.  Round 2: everything data-sized runs in libmss_b200.so kernels -
 ``mss_class_boxes`` (all boxes in one pass), ``mss_mask_edges``, ``mss_edt_row_mask`` + ``mss_edt_pass`` x 2,
 ``mss_select2`` (the order statistics np.percentile interpolates, by radix histograms masked with the surface: no boolean
-gather, no sort) - with one host sync for the boxes and one device-to-host copy of the results."""
+gather, no sort) - with one host sync for the boxes and one device-to-host copy of the results.  The 2 K directed
+distances are independent, and one envelope pass of the distance transform fills only part of the GPU (one thread per line:
+0.6 waves of CTAs at a third of the issue rate), so they are spread over a few CUDA streams and run side by side."""
 from __future__ import annotations
 
 from typing import Any, Optional, Tuple
@@ -98,6 +100,17 @@ def _directed_value(row: np.ndarray, n_to: int, percentile: Optional[float]) -> 
     return _np_lerp(a, b, n, float(percentile))
 
 
+_N_STREAMS = 4  # directed distances in flight together (each holds four int32 volumes of its class's box)
+_STREAMS: dict = {}
+
+
+def _side_streams(device: torch.device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(_N_STREAMS)]
+    return _STREAMS[key]
+
+
 def class_boxes(pred: torch.Tensor, label: torch.Tensor, n_classes: int) -> np.ndarray:
     """``generate_spatial_bounding_box`` of ``(pred == c) | (label == c)`` for every class in ONE launch and one D2H:
     int32 ``[K, 6]`` = lo (3) then hi (3, exclusive); lo > hi where the class occurs in neither map."""
@@ -131,8 +144,13 @@ def hausdorff_distance(pred: torch.Tensor, label: torch.Tensor, n_classes: int, 
         boxes = class_boxes(p, y, n_classes)
         res = torch.zeros((len(classes), 2, 4), dtype=torch.int64, device=p.device)   # uint64 bit patterns (values < 2^63)
         n_to = torch.zeros((len(classes), 2), dtype=torch.int64, device=p.device)
-        scratch = torch.empty(int(lib.mss_select_scratch_bytes()) // 8 + 1, dtype=torch.int64, device=p.device)
-        present = []
+        main = torch.cuda.current_stream()
+        streams = _side_streams(p.device)
+        n_scr = int(lib.mss_select_scratch_bytes()) // 8 + 1
+        scratch = torch.empty((len(streams), n_scr), dtype=torch.int64, device=p.device)  # one select scratch per stream
+        present, keep, job = [], [], 0
+        for s in streams:
+            s.wait_stream(main)  # res / n_to / scratch exist before a side stream touches them
         for i, c in enumerate(classes):
             lo, hi = tuple(int(v) for v in boxes[c, :3]), tuple(int(v) for v in boxes[c, 3:])
             present.append(all(h > l for l, h in zip(lo, hi)))
@@ -140,10 +158,19 @@ def hausdorff_distance(pred: torch.Tensor, label: torch.Tensor, n_classes: int, 
                 continue
             ep = _edges(p, c, lo, hi)
             ey = _edges(y, c, lo, hi)
-            _directed_async(ep, ey, quant, res[i, 0], scratch, n_to[i, 0])
-            if not directed:
-                _directed_async(ey, ep, quant, res[i, 1], scratch, n_to[i, 1])
+            keep.append((ep, ey))  # allocated on the main stream, read on side streams: alive until those have been joined
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for d, (e_from, e_to) in enumerate(((ep, ey), (ey, ep))[: 1 if directed else 2]):
+                s = streams[job % len(streams)]
+                s.wait_event(ready)
+                with torch.cuda.stream(s):
+                    _directed_async(e_from, e_to, quant, res[i, d], scratch[job % len(streams)], n_to[i, d])
+                job += 1
+        for s in streams:
+            main.wait_stream(s)
         res_h, n_to_h = res.cpu().numpy(), n_to.cpu().numpy()
+        del keep
     out = []
     for i, _c in enumerate(classes):
         if not present[i]:

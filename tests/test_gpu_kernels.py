@@ -378,6 +378,36 @@ def test_hausdorff95_bit_exact_vs_monai_restated(shape, k, seed):
     assert np.array_equal(gotf, want, equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", [(12, 14, 37), (9, 20, 64), (6, 7, 155), (5, 33, 8), (20, 5, 19)])
+def test_mask_edges_packed_kernel_vs_erosion(shape):
+    """mss_mask_edges (8 voxels per thread on packed bytes, word loads at every alignment) vs binary_erosion XOR mask on
+    the cropped box (scipy, border_value 0, thin axes squeezed away - MONAI get_mask_edges): whole volumes, boxes at odd
+    offsets, boxes one voxel thick, rows shorter than a run."""
+    from scipy import ndimage
+    from medicalsemseg_b200.hausdorff import _edges
+    rs = np.random.RandomState(sum(shape))
+    lab = _blobby(rs, shape, 3)
+    lab[rs.random_sample(shape) < 0.05] = 2
+    dev = torch.from_numpy(lab).cuda()
+    boxes = [((0, 0, 0), shape)]
+    for _ in range(12):
+        lo = tuple(int(rs.randint(0, n)) for n in shape)
+        hi = tuple(int(rs.randint(l + 1, n + 1)) for l, n in zip(lo, shape))
+        boxes.append((lo, hi))
+    boxes.append(((1, 1, 1), (2, shape[1], shape[2])))             # one plane
+    boxes.append(((0, 2, 3), (shape[0], 3, shape[2] - 1)))         # one row per plane
+    boxes.append(((0, 0, shape[2] - 1), (shape[0], shape[1], shape[2])))  # one column
+    for lo, hi in boxes:
+        for c in (0, 1, 2):
+            m = lab[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] == c
+            sq = np.squeeze(m)
+            if sq.ndim == 0:
+                continue  # 0-d erosion: not defined by the reference
+            want = (ndimage.binary_erosion(sq) ^ sq).reshape(m.shape)
+            got = _edges(dev, c, lo, hi).cpu().numpy()
+            assert np.array_equal(got.astype(bool), want) and got.max() <= 1, (lo, hi, c)
+
+
 def test_squared_edt_matches_scipy_and_properties():
     from scipy import ndimage
     from medicalsemseg_b200.hausdorff import squared_edt
