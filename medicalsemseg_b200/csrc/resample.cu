@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const __grid_constan
         }
     }
     const uint8_t* in_end = p.in + p.n_volumes * p.in_dims[0] * p.in_dims[1] * static_cast<long long>(izd);
-    const int nvec = p.slot_pitch / 16;
     const int pass_rows = p.rp * kRowsPerThread;
 
     for (int row0 = row_begin; row0 < row_end; row0 += pass_rows) {
@@ -224,6 +223,7 @@ struct StreamParams {
     int P, RS, NS;      // chunks and rows per period, period slots per CTA
     int periods;        // ceil(n_rows / RS)
     int per_block;      // periods per CTA (a multiple of NS)
+    int pf;             // periods the L2 prefetch runs ahead (0 = none)
 };
 
 // one output row's source: advanced by a fixed number of rows per step
@@ -282,18 +282,17 @@ struct ChunkStore<4> {
     static __device__ __forceinline__ void st(uint8_t* d, const unsigned* w) { *reinterpret_cast<unsigned*>(d) = w[0]; }
 };
 
-template <int CB>
-__global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_constant__ StreamParams p) {
+// The loop of one thread.  CROSS = the thread's chunk straddles a row boundary (two source rows, a select per byte);
+// the threads of a slot are ordered so that the few chunks that do (RS - 1 of P) sit in their own warps.
+template <int CB, bool CROSS>
+__device__ __forceinline__ void stream_loop(const StreamParams& p, int c, int sub) {
     constexpr int NW = CB / 4;
-    const int tid = threadIdx.x;
-    const int sub = tid / p.P, c = tid - sub * p.P;
-    if (sub >= p.NS) return;
     const int oz = p.out_dims[2];
     const int ro = (c * CB) / oz, z0 = c * CB - ro * oz;
-    const int n_first = min(CB, oz - z0);  // bytes of the chunk that lie in its first row (oz >= CB: at most two rows)
+    const int n_first = CROSS ? oz - z0 : CB;  // bytes of the chunk that lie in its first row (oz >= CB: at most two rows)
     // the fixed gather plan
-    unsigned off[CB], second[CB];  // z source offset; all ones when the byte belongs to the chunk's second row
-    unsigned keep0[NW], keep1[NW];  // byte masks of the real voxels of the first / second row
+    unsigned off[CB], second[CROSS ? CB : 1];  // z source offset; all ones when the byte belongs to the chunk's second row
+    unsigned keep0[NW], keep1[NW];             // byte masks of the real voxels of the first / second row
     bool clean = true;
 #pragma unroll
     for (int q = 0; q < NW; ++q) keep0[q] = keep1[q] = 0u;
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_const
         z = z >= oz ? z - oz : z;
         const int i = __ldg(p.iz + z);
         off[e] = i < 0 ? 0u : static_cast<unsigned>(i);
-        second[e] = e < n_first ? 0u : ~0u;
+        if (CROSS) second[e] = e < n_first ? 0u : ~0u;
         clean = clean && i >= 0;
         const unsigned m = i >= 0 ? 0xFFu << (8 * (e & 3)) : 0u;
         keep0[e >> 2] |= e < n_first ? m : 0u;
@@ -313,31 +312,46 @@ __global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_const
     const int end = min(p.periods, first + p.per_block);
     int per = first + sub;
     if (per >= end) return;
-    RowCursor r0, r1;
-    int row = per * p.RS + ro;  // (n_rows + RS < 2^31: checked by the host)
-    r0.init(p, row);
-    r1.init(p, row + 1);
     const int step = p.NS * p.RS;
+    int row = per * p.RS + ro;  // (n_rows + RS < 2^31: checked by the host)
+    RowCursor r0, r1, rp;
+    r0.init(p, row);
+    if (CROSS) r1.init(p, row + 1);
+    // a third cursor runs `pf` periods ahead and asks L2 for the sectors this thread will gather then: the byte loads of a
+    // period are one DRAM round trip otherwise (ncu: half of all stall samples on the first use of a loaded byte)
+    const int pf_rows = p.pf * step;
+    if (p.pf > 0) rp.init(p, row + pf_rows);
     long long o = (static_cast<long long>(per) * p.P + c) * CB;
     const long long o_step = static_cast<long long>(p.NS) * p.P * CB;
-    // software pipeline: the byte loads of the NEXT period are issued before this period's bytes are packed and stored,
-    // so a thread has two periods of loads in flight (the launch is latency-bound otherwise: one DRAM round trip per
-    // period and thread)
+    // software pipeline: the byte loads of the NEXT period are issued before this period's bytes are packed and stored
     unsigned b[CB], bn[CB];
-    bool v0, v1, vn0 = false, vn1 = false;
+    bool v0, v1 = true, vn0 = false, vn1 = true;
     auto fetch = [&](unsigned (&dst)[CB], bool* w0, bool* w1) {
         const unsigned s0 = r0.src(p, row < p.n_rows, w0);
-        const unsigned d1 = r1.src(p, row + 1 < p.n_rows, w1) - s0;
+        unsigned d1 = 0u;
+        if (CROSS) d1 = r1.src(p, row + 1 < p.n_rows, w1) - s0;
 #pragma unroll
-        for (int e = 0; e < CB; ++e) dst[e] = __ldg(p.in + (s0 + off[e] + (d1 & second[e])));
+        for (int e = 0; e < CB; ++e) dst[e] = __ldg(p.in + (s0 + off[e] + (CROSS ? (d1 & second[e]) : 0u)));
+    };
+    auto prefetch = [&]() {
+        if (p.pf > 0) {
+            bool ok;
+            const unsigned s = rp.src(p, row + pf_rows < p.n_rows, &ok);
+            if (ok) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + (s + off[0])));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + (s + off[CROSS ? 0 : CB - 1])));
+            }
+            rp.advance(p, step);
+        }
     };
     fetch(b, &v0, &v1);
     for (;;) {
         const bool more = per + p.NS < end;
         if (more) {
+            prefetch();
             row += step;
             r0.advance(p, step);
-            r1.advance(p, step);
+            if (CROSS) r1.advance(p, step);
             fetch(bn, &vn0, &vn1);
         }
         unsigned w[NW];
@@ -362,6 +376,31 @@ __global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_const
 #pragma unroll
         for (int e = 0; e < CB; ++e) b[e] = bn[e];
     }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(512) resample_stream_kernel(const __grid_constant__ StreamParams p) {
+    const int tid = threadIdx.x;
+    // RS - 1 chunks of a period straddle a row boundary: chunk floor(k * oz / CB) for k = 1 .. RS - 1.  The slots' other
+    // chunks take the first NS * (P - RS + 1) threads, the straddling ones the threads after them.
+    const int nc = p.RS - 1, plain = p.P - nc;
+    int sub, c;
+    bool cross;
+    if (tid < p.NS * plain) {
+        sub = tid / plain;
+        c = tid - sub * plain;
+        for (int k = 1; k <= nc; ++k)  // the c-th chunk that does not straddle
+            if ((k * p.out_dims[2]) / CB <= c) ++c;
+        cross = false;
+    } else {
+        const int i = tid - p.NS * plain;
+        if (i >= p.NS * nc) return;
+        sub = i / nc;
+        c = ((i - sub * nc + 1) * p.out_dims[2]) / CB;
+        cross = true;
+    }
+    if (__any_sync(__activemask(), cross)) stream_loop<CB, true>(p, c, sub);
+    else stream_loop<CB, false>(p, c, sub);
 }
 
 __global__ void __launch_bounds__(256) resample_gather_kernel(const __grid_constant__ ResampleParams p) {
@@ -441,7 +480,7 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
     static const int force_cb = getenv("MSS_RESAMPLE_CB") ? atoi(getenv("MSS_RESAMPLE_CB")) : -1;  // tuning knob; 0 = rows kernel
     if (force_cb != 0 && (reinterpret_cast<uintptr_t>(labels_out) & 15u) == 0 &&
         static_cast<long long>(n_volumes) * in_dims[0] * in_dims[1] * in_dims[2] < (1LL << 32)) {
-        const int cands[3] = {force_cb > 0 ? force_cb : 16, 8, 4};
+        const int cands[3] = {force_cb > 0 ? force_cb : 8, 16, 4};  // 8 measured best on B200 (kernel_bench)
         for (int ci = 0; ci < 3; ++ci) {
             const int cb = cands[ci];
             if ((cb != 4 && cb != 8 && cb != 16) || out_dims[2] < cb) continue;
@@ -463,8 +502,10 @@ extern "C" int mss_resample_nearest(const uint8_t* labels_in, const int32_t in_d
             sp.iy = index_y;
             sp.iz = index_z;
             for (int a = 0; a < 3; ++a) sp.in_dims[a] = in_dims[a], sp.out_dims[a] = out_dims[a];
-            if (n_rows + sp.RS + 1 >= (1LL << 31)) continue;
+            if (n_rows >= (1LL << 30)) continue;
             sp.n_rows = static_cast<int>(n_rows);
+            static const int pf = getenv("MSS_RESAMPLE_PF") ? atoi(getenv("MSS_RESAMPLE_PF")) : 4;  // tuning knob
+            sp.pf = pf;
             sp.total = n_rows * out_dims[2];
             sp.periods = static_cast<int>((n_rows + sp.RS - 1) / sp.RS);
             // one wave: as many CTAs as are resident together (a second, partial wave would run at a fraction of the occupancy)

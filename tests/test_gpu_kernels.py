@@ -234,6 +234,23 @@ def test_resample_3d_bit_exact(name):
     assert np.array_equal(got, oresample.resample_3d(img, case["target"]))
 
 
+@pytest.mark.parametrize("oz", [3, 5, 15, 16, 17, 20, 30, 31, 100, 147, 257, 513, 1030])
+def test_resample_3d_output_widths(oz):
+    """Every row length class of the stream kernel (chunk size 4 / 8 / 16, rows per period 1 .. 16, rows shorter than a
+    chunk, periods longer than a CTA -> rows kernel) vs scipy's zoom, incl. sizes where scipy writes its constant 0."""
+    from medicalsemseg_b200.resample import resample_3d
+    rs = np.random.RandomState(oz)
+    for in_shape, tgt in (((7, 9, max(2, int(oz * 1.37))), (11, 5, oz)), ((5, 6, max(2, oz // 2 + 1)), (5, 13, oz)),
+                          ((3, 4, oz), (9, 4, oz))):
+        img = rs.randint(1, 14, in_shape).astype(np.uint8)
+        got = resample_3d(torch.from_numpy(img).cuda(), tgt).cpu().numpy()
+        assert np.array_equal(got, oresample.resample_3d(img, tgt)), (in_shape, tgt)
+    imgs = rs.randint(1, 14, (3, 6, 5, 23)).astype(np.uint8)  # a batch: rows cross volume boundaries inside a period
+    got = resample_3d(torch.from_numpy(imgs).cuda(), (4, 7, oz)).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], oresample.resample_3d(imgs[b], (4, 7, oz)))
+
+
 def test_resample_3d_batched_and_large():
     from medicalsemseg_b200.resample import resample_3d
     rs = np.random.RandomState(77)
