@@ -25,11 +25,17 @@ struct EdgeParams {
 
 // grid: x over the (y, x-chunk) pairs of one plane of the box, y over its planes.  A thread decides kEdgeRun = 8 voxels
 // of a row at once on packed bytes: the five rows it needs (centre, +-1 row, +-1 plane) come in as aligned 32-bit words
-// funnel-shifted to the run's first byte, `byte == class` is one SIMD compare per word, the W neighbours are the centre
+// funnel-shifted to the run's first byte, `byte == class` is a zero-byte test of `word ^ class` (the six neighbours are OR-ed
+// first, so a word costs one test), the W neighbours are the centre
 // row's words shifted by one byte, and a run without a single voxel of the class (most runs of an organ's box) stops
 // after the centre row.  ~60 instructions per 8 voxels where the voxel-by-voxel form (mask_edge_at, kept for the first
 // and last bytes of the volume and as the host-checked definition) spent ~25 per voxel.
 constexpr int kEdgeRun = 8;
+
+// 0x80 in every byte of x that is zero (exact: no carries cross byte lanes)
+__device__ __forceinline__ unsigned zero_bytes(unsigned x) {
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
 
 // bytes [0, 8) at `ptr` (any alignment) as two little-endian words, from aligned word loads
 __device__ __forceinline__ uint2 load_run8(const uint8_t* ptr) {
@@ -68,40 +74,40 @@ __global__ void __launch_bounds__(256) mask_edges_kernel(const __grid_constant__
                 const int nv = x1 - x0;
                 const unsigned v0 = nv >= 4 ? 0xFFFFFFFFu : (1u << (8 * nv)) - 1u;
                 const unsigned v1 = nv >= 8 ? 0xFFFFFFFFu : (nv > 4 ? (1u << (8 * (nv - 4))) - 1u : 0u);
-                const unsigned c0 = __vcmpeq4(__funnelshift_r(lo, mid, 8), cls4) & v0;
-                const unsigned c1 = __vcmpeq4(__funnelshift_r(mid, hi, 8), cls4) & v1;
+                // byte == class  <=>  (byte ^ class) == 0; zero_bytes() marks those bytes with 0x80
+                const unsigned c0 = zero_bytes(__funnelshift_r(lo, mid, 8) ^ cls4) & v0;
+                const unsigned c1 = zero_bytes(__funnelshift_r(mid, hi, 8) ^ cls4) & v1;
                 if (c0 | c1) {
-                    unsigned in0 = 0xFFFFFFFFu, in1 = 0xFFFFFFFFu;  // bytes whose existing neighbours are all of the class
+                    // t: OR of (neighbour ^ class) over the neighbours that exist - a zero byte = every neighbour is of the
+                    // class; a neighbour outside the box is background: its byte is forced non-zero
+                    unsigned t0 = 0u, t1 = 0u;
                     if (p.n[2] > 1) {
-                        unsigned l0 = __vcmpeq4(lo, cls4), l1 = __vcmpeq4(mid, cls4);
-                        unsigned r0 = __vcmpeq4(__funnelshift_r(lo, mid, 16), cls4), r1 = __vcmpeq4(__funnelshift_r(mid, hi, 16), cls4);
-                        if (x0 == 0) l0 &= 0xFFFFFF00u;  // outside the box: background
-                        // the voxel at x = n - 1 has no right neighbour inside the box
-                        const int xl = p.n[2] - 1 - x0;
-                        if (xl < 4) r0 &= ~(0xFFu << (8 * xl));
-                        else if (xl < 8) r1 &= ~(0xFFu << (8 * (xl - 4)));
-                        in0 &= l0 & r0;
-                        in1 &= l1 & r1;
+                        t0 = (lo ^ cls4) | (__funnelshift_r(lo, mid, 16) ^ cls4);
+                        t1 = (mid ^ cls4) | (__funnelshift_r(mid, hi, 16) ^ cls4);
+                        if (x0 == 0) t0 |= 0xFFu;
+                        const int xl = p.n[2] - 1 - x0;  // the voxel at x = n - 1 has no right neighbour inside the box
+                        if (xl < 4) t0 |= 0xFFu << (8 * xl);
+                        else if (xl < 8) t1 |= 0xFFu << (8 * (xl - 4));
                     }
                     if (p.n[1] > 1) {
                         if (y == 0 || y == p.n[1] - 1) {
-                            in0 = in1 = 0u;
+                            t0 = t1 = 0xFFFFFFFFu;
                         } else {
                             const uint2 u = load_run8(c - sy), d = load_run8(c + sy);
-                            in0 &= __vcmpeq4(u.x, cls4) & __vcmpeq4(d.x, cls4);
-                            in1 &= __vcmpeq4(u.y, cls4) & __vcmpeq4(d.y, cls4);
+                            t0 |= (u.x ^ cls4) | (d.x ^ cls4);
+                            t1 |= (u.y ^ cls4) | (d.y ^ cls4);
                         }
                     }
                     if (p.n[0] > 1) {
                         if (z == 0 || z == p.n[0] - 1) {
-                            in0 = in1 = 0u;
+                            t0 = t1 = 0xFFFFFFFFu;
                         } else {
                             const uint2 u = load_run8(c - sz), d = load_run8(c + sz);
-                            in0 &= __vcmpeq4(u.x, cls4) & __vcmpeq4(d.x, cls4);
-                            in1 &= __vcmpeq4(u.y, cls4) & __vcmpeq4(d.y, cls4);
+                            t0 |= (u.x ^ cls4) | (d.x ^ cls4);
+                            t1 |= (u.y ^ cls4) | (d.y ^ cls4);
                         }
                     }
-                    const unsigned e0 = c0 & ~in0 & 0x01010101u, e1 = c1 & ~in1 & 0x01010101u;
+                    const unsigned e0 = (c0 & ~zero_bytes(t0)) >> 7, e1 = (c1 & ~zero_bytes(t1)) >> 7;
                     packed = static_cast<unsigned long long>(e0) | (static_cast<unsigned long long>(e1) << 32);
                 }
             } else {

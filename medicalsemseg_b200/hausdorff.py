@@ -13,6 +13,7 @@ distances are independent, and one envelope pass of the distance transform fills
 0.6 waves of CTAs at a third of the issue rate), so they are spread over a few CUDA streams and run side by side."""
 from __future__ import annotations
 
+import os
 from typing import Any, Optional, Tuple
 
 import numpy as np
@@ -100,7 +101,7 @@ def _directed_value(row: np.ndarray, n_to: int, percentile: Optional[float]) -> 
     return _np_lerp(a, b, n, float(percentile))
 
 
-_N_STREAMS = 4  # directed distances in flight together (each holds four int32 volumes of its class's box)
+_N_STREAMS = int(os.environ.get("MSS_HD_STREAMS", "4"))  # directed distances in flight together (each holds four int32 volumes of its class's box)
 _STREAMS: dict = {}
 
 
