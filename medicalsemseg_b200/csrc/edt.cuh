@@ -73,13 +73,28 @@ MSS_EDT_HD void edt_line_mask(const unsigned char* m, int* out, int* s, int* t, 
     edt_line_fn<Idx>([m, stride](int u) -> long long { return m[u * stride] ? 0 : kEdtInf; }, out, s, t, n, stride);
 }
 
+// floor(a / (2 k)) for 0 <= a < 2^31, 1 <= k < 2^15, from the reciprocal r = ceil(2^31 / k) = ceil(2^32 / (2 k)): the high word
+// of a * r is the quotient or one above it (a * r / 2^32 = a / (2 k) + a * e / (2 k * 2^32) with e < 2 k, an excess below 1 / 2),
+// one multiply-back decides.  Replaces the ~30-instruction emulated integer division (I2F, MUFU.RCP, F2I, two multiply-highs
+// and corrections) the envelope paid per pushed parabola.
+MSS_EDT_HD unsigned edt_recip(unsigned k) { return (0x80000000u + k - 1u) / k; }
+MSS_EDT_HD unsigned edt_div2k(unsigned a, unsigned k, unsigned r) {
+#ifdef __CUDA_ARCH__
+    unsigned q = __umulhi(a, r);
+#else
+    unsigned q = static_cast<unsigned>((static_cast<unsigned long long>(a) * r) >> 32);
+#endif
+    return q * (2u * k) > a ? q - 1u : q;
+}
+
 // The same lower envelope with the TOP of the parabola stack kept in registers: a push spills the old top (one packed
 // position / take-over word into st[], its value into hv[] - two independent stores nobody waits for), only a pop loads
 // (the entry below).  In the common case - the new parabola just joins the envelope - an iteration touches no scratch
 // memory at all, where edt_line_fn pays two dependent round trips (s[q], then h[s[q]]).  Positions and take-over points
 // are < 2^14 (volume sides < 16384), so both fit one 32-bit word.  Same comparisons, same integer arithmetic, same result.
+// `recip` (optional): edt_recip(k) for 0 < k < n, e.g. a shared-memory table built once per CTA - then no division is executed.
 template <typename Idx, typename HFn>
-MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx stride) {
+MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx stride, const unsigned* recip = nullptr) {
     int q = -1;                       // index of the top entry (entries 0 .. q-1 live in st / hv)
     // 32-bit arithmetic throughout: positions < 2^14, finite values < 2^29, so (x - i)^2 + h < 2^28 + 2^29 < 2^31
     int ts = 0, tt = 0, th = 0;  // the top: position, take-over point, value
@@ -89,10 +104,7 @@ MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int k = 0; k < kAhead; ++k) {
-            const long long v = u0 + k < n ? h(u0 + k) : static_cast<long long>(kEdtInf);
-            hb[k] = v < kEdtInf ? static_cast<int>(v) : kEdtInf;
-        }
+        for (int k = 0; k < kAhead; ++k) hb[k] = u0 + k < n ? static_cast<int>(h(u0 + k)) : kEdtInf;  // (values > kEdtInf: "none" too)
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -121,7 +133,14 @@ MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx
                 th = hu;
             } else {
                 const int num = u * u - ts * ts + hu - th, den = 2 * (u - ts);
-                int w = num >= 0 ? num / den : -((-num + den - 1) / den);  // floor division
+                int w;  // floor(num / den)
+                if (recip != nullptr) {
+                    const unsigned k = static_cast<unsigned>(u - ts), r = recip[k];
+                    w = num >= 0 ? static_cast<int>(edt_div2k(static_cast<unsigned>(num), k, r))
+                                 : -static_cast<int>(edt_div2k(static_cast<unsigned>(-num + den - 1), k, r));
+                } else {
+                    w = num >= 0 ? num / den : -((-num + den - 1) / den);
+                }
                 w += 1;
                 if (w < n) {
                     st[q * stride] = ts | (tt << 16);
@@ -152,13 +171,13 @@ MSS_EDT_HD void edt_line_cached_fn(HFn h, int* out, int* st, int* hv, int n, Idx
 }
 
 template <typename Idx>
-MSS_EDT_HD void edt_line_cached(const int* h, int* out, int* st, int* hv, int n, Idx stride) {
-    edt_line_cached_fn<Idx>([h, stride](int u) -> long long { return h[u * stride]; }, out, st, hv, n, stride);
+MSS_EDT_HD void edt_line_cached(const int* h, int* out, int* st, int* hv, int n, Idx stride, const unsigned* recip = nullptr) {
+    edt_line_cached_fn<Idx>([h, stride](int u) -> int { return h[u * stride]; }, out, st, hv, n, stride, recip);
 }
 
 template <typename Idx>
 MSS_EDT_HD void edt_line_mask_cached(const unsigned char* m, int* out, int* st, int* hv, int n, Idx stride) {
-    edt_line_cached_fn<Idx>([m, stride](int u) -> long long { return m[u * stride] ? 0 : kEdtInf; }, out, st, hv, n, stride);
+    edt_line_cached_fn<Idx>([m, stride](int u) -> int { return m[u * stride] ? 0 : kEdtInf; }, out, st, hv, n, stride);
 }
 
 // First pass along a line straight from a feature mask without any envelope: the squared distance to the nearest

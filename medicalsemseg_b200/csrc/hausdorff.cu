@@ -140,21 +140,31 @@ struct EdtParams {
     int axis;
 };
 
+constexpr int kEdtRecipMax = 2048;  // line lengths up to this divide by table (8 KB of shared memory)
+
+// MASK: the line values come from a uint8 feature mask; RECIP: line length <= kEdtRecipMax, the envelope's floor divisions
+// run on a shared-memory table of reciprocals (csrc/edt.cuh::edt_div2k) built once per CTA
+template <bool MASK, bool RECIP>
 __global__ void __launch_bounds__(128) edt_pass_kernel(const __grid_constant__ EdtParams p) {
+    __shared__ unsigned s_recip[RECIP ? kEdtRecipMax : 1];
     const long long sy = p.n[2], sz = static_cast<long long>(p.n[1]) * p.n[2];
     long long lines, stride;
     int len;
     if (p.axis == 0) lines = sz, stride = sz, len = p.n[0];
     else if (p.axis == 1) lines = static_cast<long long>(p.n[0]) * p.n[2], stride = sy, len = p.n[1];
     else lines = static_cast<long long>(p.n[0]) * p.n[1], stride = 1, len = p.n[2];
+    if (RECIP) {
+        for (int k = threadIdx.x; k < len; k += blockDim.x) s_recip[k] = k ? edt_recip(static_cast<unsigned>(k)) : 0u;
+        __syncthreads();
+    }
     for (long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; l < lines;
          l += static_cast<long long>(gridDim.x) * blockDim.x) {
         long long o;
         if (p.axis == 0) o = l;
         else if (p.axis == 1) o = (l / p.n[2]) * sz + (l % p.n[2]);
         else o = l * p.n[2];
-        if (p.mask != nullptr) edt_line_mask_cached<long long>(p.mask + o, p.out + o, p.s + o, p.t + o, len, stride);
-        else edt_line_cached<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride);
+        if (MASK) edt_line_mask_cached<long long>(p.mask + o, p.out + o, p.s + o, p.t + o, len, stride);
+        else edt_line_cached<long long>(p.in + o, p.out + o, p.s + o, p.t + o, len, stride, RECIP ? s_recip : nullptr);
     }
 }
 
@@ -324,7 +334,10 @@ static int edt_pass_impl(const int32_t* in, const uint8_t* mask, int32_t* out, i
     const long long lines = static_cast<long long>(dims[0]) * dims[1] * dims[2] / dims[axis];
     long long blocks = (lines + 127) / 128;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
-    edt_pass_kernel<<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(p);
+    const unsigned nb = static_cast<unsigned>(blocks);
+    if (mask != nullptr) edt_pass_kernel<true, false><<<nb, 128, 0, as_stream(stream)>>>(p);
+    else if (dims[axis] <= kEdtRecipMax) edt_pass_kernel<false, true><<<nb, 128, 0, as_stream(stream)>>>(p);
+    else edt_pass_kernel<false, false><<<nb, 128, 0, as_stream(stream)>>>(p);
     MSS_CUDA(cudaGetLastError());
     return MSS_OK;
 }

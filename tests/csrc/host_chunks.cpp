@@ -106,21 +106,37 @@ extern "C" void host_edt_squared(const uint8_t* feature, int d, int h, int w, in
 
 // the order and the routines the GPU driver uses since round 2: row scan along W from the mask, then the envelope with
 // the register-cached stack top along H and D
-extern "C" void host_edt_squared_v2(const uint8_t* feature, int d, int h, int w, int* out) {
+// use_recip: divide by the reciprocal table (what the pass kernel does for lines up to 2048 voxels)
+extern "C" void host_edt_squared_v2(const uint8_t* feature, int d, int h, int w, int use_recip, int* out) {
     const long long n = static_cast<long long>(d) * h * w;
     std::vector<int> a(n), b(n), s(n), t(n);
+    std::vector<unsigned> recip(static_cast<size_t>(d > h ? d : h) + 1, 0u);
+    for (size_t k = 1; k < recip.size(); ++k) recip[k] = mss::edt_recip(static_cast<unsigned>(k));
+    const unsigned* rp = use_recip ? recip.data() : nullptr;
     for (long long r = 0; r < static_cast<long long>(d) * h; ++r) mss::edt_row_from_mask(feature + r * w, a.data() + r * w, w);
     for (int z = 0; z < d; ++z)
         for (int x = 0; x < w; ++x) {
             const long long o = static_cast<long long>(z) * h * w + x;
-            mss::edt_line_cached<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, h, w);
+            mss::edt_line_cached<long long>(a.data() + o, b.data() + o, s.data() + o, t.data() + o, h, w, rp);
         }
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             const long long o = static_cast<long long>(y) * w + x;
-            mss::edt_line_cached<long long>(b.data() + o, a.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w);
+            mss::edt_line_cached<long long>(b.data() + o, a.data() + o, s.data() + o, t.data() + o, d, static_cast<long long>(h) * w, rp);
         }
     for (long long i = 0; i < n; ++i) out[i] = a[i];
+}
+
+// edt_div2k against the plain floor division over a strided sweep of numerators for every k < kmax: returns the mismatches
+extern "C" long long host_edt_div_check(int kmax, unsigned step) {
+    long long bad = 0;
+    for (unsigned k = 1; k < static_cast<unsigned>(kmax); ++k) {
+        const unsigned r = mss::edt_recip(k);
+        for (unsigned long long a = 0; a < (1ull << 31); a += step + k) bad += mss::edt_div2k(static_cast<unsigned>(a), k, r) != a / (2 * k);
+        for (unsigned a = (1u << 31) - 4096; a < (1u << 31); ++a) bad += mss::edt_div2k(a, k, r) != a / (2 * k);
+        for (unsigned a = 0; a < 8 * k + 8; ++a) bad += mss::edt_div2k(a, k, r) != a / (2 * k);
+    }
+    return bad;
 }
 
 // surface voxels of class cls inside the box [lo, hi) of a label map [dims], as csrc/hausdorff.cu computes them

@@ -88,7 +88,9 @@ def test_edt_line_routine_matches_scipy(lib, shape, density):
     lib.host_edt_squared(feat.ctypes.data, shape[0], shape[1], shape[2], out.ctypes.data)
     # round 2: row scan from the mask + the envelope with the register-cached stack top (what the GPU driver runs now)
     out2 = np.zeros(shape, np.int32)
-    lib.host_edt_squared_v2(feat.ctypes.data, shape[0], shape[1], shape[2], out2.ctypes.data)
+    lib.host_edt_squared_v2(feat.ctypes.data, shape[0], shape[1], shape[2], 0, out2.ctypes.data)
+    assert np.array_equal(out, out2)
+    lib.host_edt_squared_v2(feat.ctypes.data, shape[0], shape[1], shape[2], 1, out2.ctypes.data)  # divisions by reciprocal table
     assert np.array_equal(out, out2)
     if feat.sum() == 0:
         assert np.all(out == 1 << 29)
@@ -96,6 +98,12 @@ def test_edt_line_routine_matches_scipy(lib, shape, density):
     want = ndimage.distance_transform_edt(feat == 0)
     assert np.array_equal(np.sqrt(out.astype(np.float64)), want)
     assert np.array_equal(out, np.rint(want ** 2).astype(np.int32))
+
+
+def test_edt_reciprocal_division_is_exact(lib):
+    """edt_div2k(a, k, ceil(2^31 / k)) == a // (2 k) over a strided sweep of a < 2^31 (plus both ends) for every k < 2048."""
+    lib.host_edt_div_check.restype = C.c_longlong
+    assert lib.host_edt_div_check(2048, 99991) == 0
 
 
 def _blobby_labels(rs, shape, k):
