@@ -55,6 +55,9 @@ extern "C" {
 /* what mss_accumulate does with a voxel once its last covering window has been applied */
 #define MSS_FUSE_NONE 0   /* keep raw weighted sums (multi-GPU slabs: halo exchange comes first)  */
 #define MSS_FUSE_LOGITS 1 /* store sum / count  (engine/utils.py:151)                             */
+#define MSS_ACC_PATH_GENERAL 0 /* mss_accumulate_last_path(): per-quad general kernel               */
+#define MSS_ACC_PATH_CELLS 1   /* cell-uniform kernel (per-thread cp.async rings)                   */
+#define MSS_ACC_PATH_ROWS 2    /* row-staged kernel (bulk copies; K <= 4, one launch, labels out)   */
 #define MSS_FUSE_LABELS 2 /* store only the uint8 argmax label (engine/test.py:140-141)          */
 
 /*
@@ -153,6 +156,10 @@ int mss_accumulate_range(const mss_layout_t* lay, const void* const* batch_ptrs,
                          int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
                          int64_t own_first, int64_t own_count, const float* importance_map, float* acc,
                          void* stream);
+
+/* Which kernel the calling thread's last successful mss_accumulate / mss_accumulate_range call launched (MSS_ACC_PATH_*;
+ * -1 before the first call): lets tests and benches state which path they measured.  No reference counterpart. */
+int mss_accumulate_last_path(void);
 
 /* Normalise + softmax-argmax -> uint8 (engine/utils.py:151 + engine/test.py:140-141) over the local
  * box [box_lo, box_hi) of `logits[Nb, K, extent_d, extent_h, pitch_w]`.  normalise != 0 divides by

@@ -41,6 +41,7 @@ class MssError(RuntimeError):
 _SIGNATURES = {
     "mss_abi_version": (C.c_int, []),
     "mss_last_error": (C.c_char_p, []),
+    "mss_accumulate_last_path": (C.c_int, []),
     "mss_axis_starts": (C.c_int, [c_i32, c_i32, c_i32, C.POINTER(c_i32), c_i32]),
     "mss_geom_table_len": (c_i64, [I3, I3]),
     "mss_geom_table_build": (C.c_int, [I3, I3, I3, vp, vp, vp, vp, c_i64]),

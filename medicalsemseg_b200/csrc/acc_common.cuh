@@ -142,6 +142,9 @@ constexpr size_t acc_smem_bytes() {
 }
 
 
+// accumulate_rows.cu (few classes, every window in one launch, labels out)
+int launch_rows(const mss_layout_t* lay, const AccParams& p, int logits_dtype, cudaStream_t s, cudaError_t* err);
+
 // accumulate_cells.cu
 int launch_cells(const mss_layout_t* lay, const AccParams& p, int logits_dtype, cudaStream_t s, cudaError_t* err);
 

@@ -395,6 +395,8 @@ static cudaError_t launch_for_k(int K, dim3 grid, cudaStream_t s, const AccParam
 
 using namespace mss;
 
+static thread_local int t_last_path = -1;  // which kernel the calling thread's last accumulate call launched
+
 static int accumulate_impl(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
                            int32_t logits_dtype, int64_t first_window, int64_t n_windows, int64_t own_first,
                            int64_t own_count, const float* importance_map, float* acc, int32_t fuse, uint8_t* labels,
@@ -492,11 +494,18 @@ static int accumulate_impl(const mss_layout_t* lay, const void* const* batch_ptr
     p.b_lo = b_lo;
     p.nq = (p.box_n[2] + 3) / 4;
     cudaStream_t s = as_stream(stream);
-    // the cell-uniform kernel (accumulate_cells.cu) serves every geometry that fits its tables; the general kernel the rest
+    // few classes, every window in this launch, labels out: the row-staged kernel (accumulate_rows.cu); otherwise the
+    // cell-uniform kernel (accumulate_cells.cu) serves every geometry that fits its tables, and the general kernel the rest
     {
         cudaError_t cerr = cudaSuccess;
+        if (launch_rows(lay, p, logits_dtype, s, &cerr) == 0) {
+            MSS_CUDA(cerr);
+            t_last_path = MSS_ACC_PATH_ROWS;
+            return MSS_OK;
+        }
         if (launch_cells(lay, p, logits_dtype, s, &cerr) == 0) {
             MSS_CUDA(cerr);
+            t_last_path = MSS_ACC_PATH_CELLS;
             return MSS_OK;
         }
     }
@@ -516,8 +525,11 @@ static int accumulate_impl(const mss_layout_t* lay, const void* const* batch_ptr
     else
         e = launch_for_k<__nv_bfloat16>(g.K, grid, s, p);
     MSS_CUDA(e);
+    t_last_path = MSS_ACC_PATH_GENERAL;
     return MSS_OK;
 }
+
+extern "C" int mss_accumulate_last_path(void) { return t_last_path; }
 
 extern "C" int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches, int32_t sw_batch,
                               int32_t logits_dtype, int64_t first_window, int64_t n_windows, const float* importance_map,

@@ -90,6 +90,26 @@ def test_fused_labels_vs_oracle(name, group_bytes):
         assert st.accumulator_allocated == (st.n_predictor_calls > 1)
 
 
+@pytest.mark.parametrize("name", ["basic_b1", "two_volumes", "padded_cval", "constant_mode", "brats_like", "full_axis", "overlap_zero"])
+def test_rows_kernel_serves_few_classes(name):
+    """K <= 4, every window in one launch, labels out, <= 4 window positions along W: the row-staged kernel
+    (csrc/accumulate_rows.cu: bulk copies of whole window rows into a shared-memory ring) is the one that runs - same labels
+    as the oracle, same near-tie census as the cell kernel's path (one launch per batch)."""
+    from medicalsemseg_b200 import _lib
+    case = SW_CASES[name]
+    ref, _ = oracle_run(case)
+    vol, affine = cuda_inputs(case)
+    st, st2 = mss.InferStats(), mss.InferStats()
+    kw = dict(sw_batch_size=case["sw_batch"], cval=case.get("cval", 0.0), affine=affine)
+    labels = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), case["roi"], case["overlap"], case["mode"], stats=st, **kw)
+    assert _lib.load().mss_accumulate_last_path() == 2, "expected the row-staged kernel"
+    assert assert_labels_match(labels, ref) <= 2
+    other = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), case["roi"], case["overlap"], case["mode"], stats=st2,
+                                     group_bytes=1, **kw)
+    assert st2.n_accumulate_calls == 1 or _lib.load().mss_accumulate_last_path() != 2  # several launches: the cell kernel
+    assert torch.equal(labels, other) and st.near_ties == st2.near_ties
+
+
 @pytest.mark.parametrize("name", ["aniso_ragged", "two_volumes", "padded_cval", "brats_like"])
 def test_labels_and_logits_together(name):
     case = SW_CASES[name]
