@@ -20,9 +20,9 @@ namespace mss {
 constexpr int kRowsMaxSeg = 64;    // segments / window starts per axis
 constexpr int kRowsMaxWin = 64;    // windows over one (D, H) cell, all W positions
 constexpr int kRowsMaxWinW = 4;    // W positions of the grid (small volumes: every thread's quad is covered by most of them)
-constexpr int kRowsStages = 4;    // (a power of two)
+constexpr int kRowsMaxStages = 8;
 constexpr int kRowsThreads = 256;
-constexpr int kRowsMaxTr = 16;     // rows of a tile
+constexpr int kRowsMaxTr = 64;     // rows of a tile
 constexpr int kRowsMaxRuns = 4;    // planes a tile's rows may touch (one bulk copy per plane-run)
 
 struct RowsParams {
@@ -69,10 +69,10 @@ __device__ __forceinline__ void rows_bulk_copy(float* dst, const float* src, uns
                  : "memory");
 }
 
-template <int K>
+template <int K, int S, int RPT>  // classes, ring depth (a power of two), rows per thread
 __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
-    extern __shared__ __align__(128) float ring[];  // [kRowsStages] stages of [K + 1][TR][roi_w]
-    __shared__ __align__(8) uint64_t full[kRowsStages];
+    extern __shared__ __align__(128) float ring[];  // [S] stages of [K + 1][TR][roi_w]
+    __shared__ __align__(8) uint64_t full[S];
     __shared__ const float* s_base[kRowsMaxWin];  // class-0 logits of the cell's windows, ascending window index
     __shared__ int s_term[kRowsMaxWin];           // (start_d * roi_h + start_h) * roi_w  [floats]
     __shared__ int s_sw[kRowsMaxWin];             // start_w
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kRowsStages; ++s) rows_bar_init(&full[s]);
+        for (int s = 0; s < S; ++s) rows_bar_init(&full[s]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
     const int total = ntile * nwin;
     int it = 0, ij = 0, iq = 0;  // producer cursor: step iq = (tile it, window ij)
     {
-        const int pro = min(kRowsStages, total);
+        const int pro = min(S, total);
         if (tid == 0) {
             int t = 0, j = 0;
             for (int q = 0; q < pro; ++q) {
@@ -167,79 +167,86 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
         }
     }
 
-    // ---- consumer side: 4 voxels of one row ---------------------------------------------------------------------------
+    // ---- consumer side: 4 voxels of each of RPT rows (rows r_c, r_c + TRP, ...: more rows per step = fewer steps, and a step
+    // costs a wait, an arrival, a block barrier and the copy issue whatever it carries) -----------------------------------
+    const int TRP = kRowsThreads / nq;  // rows one pass of the CTA's threads covers
     const int r_c = tid / nq, g = tid - r_c * nq;
-    const bool lane_rows = r_c < TR;
-    float4 a[K];
+    float4 a[RPT][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rr = 0; rr < RPT; ++rr)
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned ties = 0;
     int t = 0, j = 0;
     for (int q = 0; q < total; ++q) {
-        const int s = q & (kRowsStages - 1);
+        const int s = q & (S - 1);
         const int T = tile0 + t;
-        const bool active = lane_rows && T * TR + r_c < rows_cell;
         const int l = g * 4 - s_sw[j];  // window-local column of the quad's first voxel
-        rows_bar_wait(&full[s], static_cast<unsigned>((q / kRowsStages) & 1));
-        if (active && l > -4 && l < rw) {
-            const float* st = ring + static_cast<size_t>(s) * stage_floats + r_c * rw + l;
-            if (l >= 0 && l + 4 <= rw && (l & 3) == 0) {
-                const float4 w4 = *reinterpret_cast<const float4*>(st);
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float4 v = *reinterpret_cast<const float4*>(st + (k + 1) * TR * rw);
-                    a[k].x = __fadd_rn(a[k].x, __fmul_rn(w4.x, v.x));  // engine/utils.py:147, product and sum rounded separately
-                    a[k].y = __fadd_rn(a[k].y, __fmul_rn(w4.y, v.y));
-                    a[k].z = __fadd_rn(a[k].z, __fmul_rn(w4.z, v.z));
-                    a[k].w = __fadd_rn(a[k].w, __fmul_rn(w4.w, v.w));
-                }
-            } else {  // off the 16-byte lattice, or the window covers the quad partly
-                const bool c0 = l >= 0, c1 = l + 1 >= 0 && l + 1 < rw, c2 = l + 2 >= 0 && l + 2 < rw, c3 = l + 3 < rw;
-                const float w0 = c0 ? st[0] : 0.f, w1 = c1 ? st[1] : 0.f, w2 = c2 ? st[2] : 0.f, w3 = c3 ? st[3] : 0.f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float* lp = st + (k + 1) * TR * rw;
-                    if (c0) a[k].x = __fadd_rn(a[k].x, __fmul_rn(w0, lp[0]));
-                    if (c1) a[k].y = __fadd_rn(a[k].y, __fmul_rn(w1, lp[1]));
-                    if (c2) a[k].z = __fadd_rn(a[k].z, __fmul_rn(w2, lp[2]));
-                    if (c3) a[k].w = __fadd_rn(a[k].w, __fmul_rn(w3, lp[3]));
-                }
-            }
-        }
         const bool last_win = j + 1 == nwin;
-        if (active && last_win) {  // the tile's voxels are complete: first-max argmax of the raw sums
-            int d, h;
-            row_dh(T, r_c, &d, &h);
-            ArgmaxState am[4];
+        rows_bar_wait(&full[s], static_cast<unsigned>((q / S) & 1));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) am[e].reset();
+        for (int rr = 0; rr < RPT; ++rr) {
+            const int r = r_c + rr * TRP;
+            const bool active = r_c < TRP && r < TR && T * TR + r < rows_cell;
+            if (active && l > -4 && l < rw) {
+                const float* st = ring + static_cast<size_t>(s) * stage_floats + r * rw + l;
+                if (l >= 0 && l + 4 <= rw && (l & 3) == 0) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(st);
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                am[0].push(a[k].x, k);
-                am[1].push(a[k].y, k);
-                am[2].push(a[k].z, k);
-                am[3].push(a[k].w, k);
-                a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < K; ++k) {
+                        const float4 v = *reinterpret_cast<const float4*>(st + (k + 1) * TR * rw);
+                        a[rr][k].x = __fadd_rn(a[rr][k].x, __fmul_rn(w4.x, v.x));  // engine/utils.py:147: product, then sum
+                        a[rr][k].y = __fadd_rn(a[rr][k].y, __fmul_rn(w4.y, v.y));
+                        a[rr][k].z = __fadd_rn(a[rr][k].z, __fmul_rn(w4.z, v.z));
+                        a[rr][k].w = __fadd_rn(a[rr][k].w, __fmul_rn(w4.w, v.w));
+                    }
+                } else {  // off the 16-byte lattice, or the window covers the quad partly
+                    const bool c0 = l >= 0, c1 = l + 1 >= 0 && l + 1 < rw, c2 = l + 2 >= 0 && l + 2 < rw, c3 = l + 3 < rw;
+                    const float w0 = c0 ? st[0] : 0.f, w1 = c1 ? st[1] : 0.f, w2 = c2 ? st[2] : 0.f, w3 = c3 ? st[3] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float* lp = st + (k + 1) * TR * rw;
+                        if (c0) a[rr][k].x = __fadd_rn(a[rr][k].x, __fmul_rn(w0, lp[0]));
+                        if (c1) a[rr][k].y = __fadd_rn(a[rr][k].y, __fmul_rn(w1, lp[1]));
+                        if (c2) a[rr][k].z = __fadd_rn(a[rr][k].z, __fmul_rn(w2, lp[2]));
+                        if (c3) a[rr][k].w = __fadd_rn(a[rr][k].w, __fmul_rn(w3, lp[3]));
+                    }
+                }
             }
-            uint8_t* lab = p.labels + ((static_cast<long long>(b) * p.img[0] + d) * p.img[1] + h) * p.label_pitch + g * 4;
-            const int nv = min(4, W - g * 4);
-            unsigned packed = 0;
+            if (active && last_win) {  // the tile's voxels are complete: first-max argmax of the raw sums
+                int d, h;
+                row_dh(T, r, &d, &h);
+                ArgmaxState am[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
-                if (e < nv) ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
-            }
-            if (nv == 4 && (reinterpret_cast<uintptr_t>(lab) & 3u) == 0) {
-                *reinterpret_cast<unsigned*>(lab) = packed;
-            } else {
+                for (int e = 0; e < 4; ++e) am[e].reset();
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (e < nv) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+                for (int k = 0; k < K; ++k) {
+                    am[0].push(a[rr][k].x, k);
+                    am[1].push(a[rr][k].y, k);
+                    am[2].push(a[rr][k].z, k);
+                    am[3].push(a[rr][k].w, k);
+                    a[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint8_t* lab = p.labels + ((static_cast<long long>(b) * p.img[0] + d) * p.img[1] + h) * p.label_pitch + g * 4;
+                const int nv = min(4, W - g * 4);
+                unsigned packed = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    packed |= static_cast<unsigned>(am[e].label()) << (8 * e);
+                    if (e < nv) ties += am[e].near_tie(p.tie_tol) ? 1u : 0u;
+                }
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(lab) & 3u) == 0) {
+                    *reinterpret_cast<unsigned*>(lab) = packed;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < nv) lab[e] = static_cast<uint8_t>(packed >> (8 * e));
+                }
             }
         }
         if (last_win) j = 0, ++t;
         else ++j;
-        if (iq < total) {  // refill the stage just read with step q + kRowsStages (uniform over the CTA)
+        if (iq < total) {  // refill the stage just read with step q + S (uniform over the CTA)
             if (tid == 0) expect(it, s);
             __syncthreads();  // everybody has read the stage; the arrival above precedes every copy's complete_tx
             issue(it, ij, s);
@@ -327,7 +334,13 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     if (static_cast<long long>(rows_max[0]) * rows_max[1] >= (1 << 22)) return -1;
     if ((static_cast<long long>(g.img[0]) * g.roi[1] + g.img[1]) * g.roi[2] + g.img[2] >= (1LL << 31)) return -1;  // 32-bit row terms
     // tiles: as many rows as rows x quads fill the CTA; a CTA takes `tiles_per_cta` consecutive tiles of a cell
-    int tr = kRowsThreads / nq;
+    static const int force_tr = getenv("MSS_ROWS_TR") ? atoi(getenv("MSS_ROWS_TR")) : 0;  // tuning knob
+    static const int force_rpt = getenv("MSS_ROWS_RPT") ? atoi(getenv("MSS_ROWS_RPT")) : 0;     // tuning knob
+    const int rpt = force_rpt == 1 || force_rpt == 4 ? force_rpt : 2;
+    int trp = kRowsThreads / nq;
+    trp = trp > 16 ? 16 : trp;
+    int tr = rpt * trp;
+    if (force_tr > 0 && force_tr < tr) tr = force_tr;
     tr = tr > kRowsMaxTr ? kRowsMaxTr : tr;
     int n1_min = 1 << 30;
     for (int i = 0; i < p.n_seg[1]; ++i) n1_min = p.seg_n[1][i] < n1_min ? p.seg_n[1][i] : n1_min;
@@ -337,12 +350,14 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     const int tiles_cell = (rows_cell_max + tr - 1) / tr;
     const long long tiles_total = static_cast<long long>(tiles_cell) * p.n_seg[0] * p.n_seg[1] * g.nb;
     static const int force_tpc = getenv("MSS_ROWS_TPC") ? atoi(getenv("MSS_ROWS_TPC")) : 0;  // tuning knob
-    long long tpc = tiles_total / (148LL * 4 * 4);  // ~4 waves of CTAs
+    long long tpc = tiles_total / (148LL * 32);  // ~8 waves of CTAs (measured: BraTS 2 tiles per CTA best, 1 / 4 / 8 within 10 %)
     tpc = tpc < 1 ? 1 : (tpc > 64 ? 64 : tpc);
     if (force_tpc > 0) tpc = force_tpc;
     p.tiles_per_cta = static_cast<int>(tpc);
     const long long nx = (tiles_cell + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    const size_t smem = static_cast<size_t>(kRowsStages) * (g.K + 1) * tr * g.roi[2] * sizeof(float);
+    static const int force_st = getenv("MSS_ROWS_STAGES") ? atoi(getenv("MSS_ROWS_STAGES")) : 0;  // tuning knob
+    const int stages = force_st == 8 ? 8 : 4;
+    const size_t smem = static_cast<size_t>(stages) * (g.K + 1) * tr * g.roi[2] * sizeof(float);
     const long long nz = static_cast<long long>(g.nb) * p.n_seg[0];
     if (nx <= 0 || nx > 0x7fffffffLL || nz > 65535 || smem > 200 * 1024) return -1;
     const dim3 grid(static_cast<unsigned>(nx), static_cast<unsigned>(p.n_seg[1]), static_cast<unsigned>(nz));
@@ -352,12 +367,20 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
         kernel<<<grid, kRowsThreads, smem, s>>>(p);
         return cudaGetLastError();
     };
+#define MSS_ROWS_CASE(KK)                                                                      \
+    case KK:                                                                                   \
+        if (stages == 8) *err = rpt == 1 ? launch(accumulate_rows_kernel<KK, 8, 1>)             \
+                                : rpt == 2 ? launch(accumulate_rows_kernel<KK, 8, 2>) : launch(accumulate_rows_kernel<KK, 8, 4>); \
+        else *err = rpt == 1 ? launch(accumulate_rows_kernel<KK, 4, 1>)                         \
+                  : rpt == 2 ? launch(accumulate_rows_kernel<KK, 4, 2>) : launch(accumulate_rows_kernel<KK, 4, 4>); \
+        break;
     switch (g.K) {
-        case 1: *err = launch(accumulate_rows_kernel<1>); break;
-        case 2: *err = launch(accumulate_rows_kernel<2>); break;
-        case 3: *err = launch(accumulate_rows_kernel<3>); break;
-        default: *err = launch(accumulate_rows_kernel<4>); break;
+        MSS_ROWS_CASE(1)
+        MSS_ROWS_CASE(2)
+        MSS_ROWS_CASE(3)
+        MSS_ROWS_CASE(4)
     }
+#undef MSS_ROWS_CASE
     return 0;
 }
 
