@@ -1,5 +1,6 @@
 // Row-staged weighted overlap accumulation + argmax for FEW classes (engine/utils.py:137-151 + engine/test.py:140-141):
-// the path of a K <= 4 model (cfg4: BraTS, K = 3) whose windows all sit in one launch, labels out, no accumulator.
+// the path of a K <= 4 model (cfg4: BraTS, K = 3) whose windows all sit in one launch: labels (or the normalised logits) straight
+// out, no accumulator round trip.
 //
 // Why a third accumulation kernel: with few classes the cell kernel (accumulate_cells.cu) is instruction-bound - a thread
 // issues its own 16-byte cp.async per class, plane and window (four 4-byte copies for a window that starts off the 16-byte
@@ -20,7 +21,6 @@ namespace mss {
 constexpr int kRowsMaxSeg = 64;    // segments / window starts per axis
 constexpr int kRowsMaxWin = 64;    // windows over one (D, H) cell, all W positions
 constexpr int kRowsMaxWinW = 4;    // W positions of the grid (small volumes: every thread's quad is covered by most of them)
-constexpr int kRowsMaxStages = 8;
 constexpr int kRowsThreads = 256;
 constexpr int kRowsMaxTr = 64;     // rows of a tile
 constexpr int kRowsMaxRuns = 4;    // planes a tile's rows may touch (one bulk copy per plane-run)
@@ -31,6 +31,8 @@ struct RowsParams {
     const float* imp;
     uint8_t* labels;
     int label_pitch;
+    float* out;   // LOGITS mode: normalised logits [Nb, K, D, H, pitch]
+    int pitch;
     float tie_tol;
     unsigned long long* near_ties;
     int roi[3], img[3], ns[3];
@@ -69,7 +71,7 @@ __device__ __forceinline__ void rows_bulk_copy(float* dst, const float* src, uns
                  : "memory");
 }
 
-template <int K, int S, int RPT>  // classes, ring depth (a power of two), rows per thread
+template <int K, int S, int RPT, bool LOGITS>  // classes, ring depth, rows per thread, sum / count out instead of labels
 __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
     extern __shared__ __align__(128) float ring[];  // [S] stages of [K + 1][TR][roi_w]
     __shared__ __align__(8) uint64_t full[S];
@@ -172,18 +174,22 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
     const int TRP = kRowsThreads / nq;  // rows one pass of the CTA's threads covers
     const int r_c = tid / nq, g = tid - r_c * nq;
     float4 a[RPT][K];
+    float4 cnt[LOGITS ? RPT : 1];  // LOGITS: the weight count (engine/utils.py:148: ascending fp32 sum of the covering windows' weights)
 #pragma unroll
-    for (int rr = 0; rr < RPT; ++rr)
+    for (int rr = 0; rr < RPT; ++rr) {
+        if (LOGITS) cnt[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < K; ++k) a[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     unsigned ties = 0;
     int t = 0, j = 0;
+    int s = 0;
+    unsigned phase = 0;  // ring stage of step q and the parity of its barrier phase
     for (int q = 0; q < total; ++q) {
-        const int s = q & (S - 1);
         const int T = tile0 + t;
         const int l = g * 4 - s_sw[j];  // window-local column of the quad's first voxel
         const bool last_win = j + 1 == nwin;
-        rows_bar_wait(&full[s], static_cast<unsigned>((q / S) & 1));
+        rows_bar_wait(&full[s], phase);
 #pragma unroll
         for (int rr = 0; rr < RPT; ++rr) {
             const int r = r_c + rr * TRP;
@@ -192,6 +198,10 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
                 const float* st = ring + static_cast<size_t>(s) * stage_floats + r * rw + l;
                 if (l >= 0 && l + 4 <= rw && (l & 3) == 0) {
                     const float4 w4 = *reinterpret_cast<const float4*>(st);
+                    if (LOGITS) {
+                        cnt[rr].x = __fadd_rn(cnt[rr].x, w4.x), cnt[rr].y = __fadd_rn(cnt[rr].y, w4.y);
+                        cnt[rr].z = __fadd_rn(cnt[rr].z, w4.z), cnt[rr].w = __fadd_rn(cnt[rr].w, w4.w);
+                    }
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const float4 v = *reinterpret_cast<const float4*>(st + (k + 1) * TR * rw);
@@ -203,6 +213,12 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
                 } else {  // off the 16-byte lattice, or the window covers the quad partly
                     const bool c0 = l >= 0, c1 = l + 1 >= 0 && l + 1 < rw, c2 = l + 2 >= 0 && l + 2 < rw, c3 = l + 3 < rw;
                     const float w0 = c0 ? st[0] : 0.f, w1 = c1 ? st[1] : 0.f, w2 = c2 ? st[2] : 0.f, w3 = c3 ? st[3] : 0.f;
+                    if (LOGITS) {
+                        if (c0) cnt[rr].x = __fadd_rn(cnt[rr].x, w0);
+                        if (c1) cnt[rr].y = __fadd_rn(cnt[rr].y, w1);
+                        if (c2) cnt[rr].z = __fadd_rn(cnt[rr].z, w2);
+                        if (c3) cnt[rr].w = __fadd_rn(cnt[rr].w, w3);
+                    }
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const float* lp = st + (k + 1) * TR * rw;
@@ -213,7 +229,25 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
                     }
                 }
             }
-            if (active && last_win) {  // the tile's voxels are complete: first-max argmax of the raw sums
+            if (active && last_win && LOGITS) {  // the tile's voxels are complete: sum / count (engine/utils.py:151)
+                int d, h;
+                row_dh(T, r, &d, &h);
+                const int nv = min(4, W - g * 4);
+                const long long cs = static_cast<long long>(p.img[0]) * p.img[1] * p.pitch;
+                float* o = p.out + static_cast<long long>(b) * K * cs + (static_cast<long long>(d) * p.img[1] + h) * p.pitch + g * 4;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float4 v = a[rr][k];
+                    v.x = __fdiv_rn(v.x, cnt[rr].x);
+                    v.y = nv > 1 ? __fdiv_rn(v.y, cnt[rr].y) : 0.f;  // (the pad voxels of a ragged row stay 0)
+                    v.z = nv > 2 ? __fdiv_rn(v.z, cnt[rr].z) : 0.f;
+                    v.w = nv > 3 ? __fdiv_rn(v.w, cnt[rr].w) : 0.f;
+                    *reinterpret_cast<float4*>(o + k * cs) = v;
+                    a[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                cnt[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (active && last_win && !LOGITS) {  // the tile's voxels are complete: first-max argmax of the raw sums
                 int d, h;
                 row_dh(T, r, &d, &h);
                 ArgmaxState am[4];
@@ -253,6 +287,7 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
             ++iq;
             if (++ij == nwin) ij = 0, ++it;
         }
+        if (++s == S) s = 0, phase ^= 1u;
     }
     if (ties && p.near_ties != nullptr) atomicAdd(p.near_ties, static_cast<unsigned long long>(ties));
 }
@@ -262,7 +297,9 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     *err = cudaSuccess;
     const Geo& g = ap.g;
     static const int disabled = getenv("MSS_ACC_NO_ROWS") ? atoi(getenv("MSS_ACC_NO_ROWS")) : 0;
-    if (disabled || logits_dtype != MSS_F32 || ap.fuse != MSS_FUSE_LABELS || !ap.vec_ok || g.K < 1 || g.K > 4) return -1;
+    if (disabled || logits_dtype != MSS_F32 || ap.fuse == MSS_FUSE_NONE || !ap.vec_ok || g.K < 1 || g.K > 4) return -1;
+    const bool logits_out = ap.fuse == MSS_FUSE_LOGITS;
+    if (logits_out && (ap.acc == nullptr || g.pitch % 4 != 0 || g.pitch < g.img[2])) return -1;
     const long long total = g.n_local * g.nb;
     if (ap.g0 != 0 || ap.g1 != total || ap.own0 != 0 || ap.own1 != total) return -1;  // every window, one launch
     for (int a = 0; a < 3; ++a)
@@ -275,6 +312,8 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     p.sw_batch = ap.sw_batch;
     p.imp = ap.imp;
     p.labels = ap.labels;
+    p.out = ap.acc;
+    p.pitch = g.pitch;
     p.label_pitch = ap.label_pitch;
     p.tie_tol = ap.tie_tol;
     p.near_ties = ap.near_ties;
@@ -356,7 +395,7 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     p.tiles_per_cta = static_cast<int>(tpc);
     const long long nx = (tiles_cell + p.tiles_per_cta - 1) / p.tiles_per_cta;
     static const int force_st = getenv("MSS_ROWS_STAGES") ? atoi(getenv("MSS_ROWS_STAGES")) : 0;  // tuning knob
-    const int stages = force_st == 8 ? 8 : 4;
+    const int stages = force_st == 2 || force_st == 4 ? force_st : 3;  // 3: 55 KB per CTA at BraTS size, 4 CTAs per SM
     const size_t smem = static_cast<size_t>(stages) * (g.K + 1) * tr * g.roi[2] * sizeof(float);
     const long long nz = static_cast<long long>(g.nb) * p.n_seg[0];
     if (nx <= 0 || nx > 0x7fffffffLL || nz > 65535 || smem > 200 * 1024) return -1;
@@ -367,12 +406,14 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
         kernel<<<grid, kRowsThreads, smem, s>>>(p);
         return cudaGetLastError();
     };
-#define MSS_ROWS_CASE(KK)                                                                      \
-    case KK:                                                                                   \
-        if (stages == 8) *err = rpt == 1 ? launch(accumulate_rows_kernel<KK, 8, 1>)             \
-                                : rpt == 2 ? launch(accumulate_rows_kernel<KK, 8, 2>) : launch(accumulate_rows_kernel<KK, 8, 4>); \
-        else *err = rpt == 1 ? launch(accumulate_rows_kernel<KK, 4, 1>)                         \
-                  : rpt == 2 ? launch(accumulate_rows_kernel<KK, 4, 2>) : launch(accumulate_rows_kernel<KK, 4, 4>); \
+#define MSS_ROWS_PICK(KK, SS, LL)                                                               \
+    (rpt == 1 ? launch(accumulate_rows_kernel<KK, SS, 1, LL>)                                   \
+              : rpt == 2 ? launch(accumulate_rows_kernel<KK, SS, 2, LL>) : launch(accumulate_rows_kernel<KK, SS, 4, LL>))
+#define MSS_ROWS_STAGED(KK, LL) \
+    (stages == 2 ? MSS_ROWS_PICK(KK, 2, LL) : stages == 3 ? MSS_ROWS_PICK(KK, 3, LL) : MSS_ROWS_PICK(KK, 4, LL))
+#define MSS_ROWS_CASE(KK)                                                       \
+    case KK:                                                                    \
+        *err = logits_out ? MSS_ROWS_STAGED(KK, true) : MSS_ROWS_STAGED(KK, false); \
         break;
     switch (g.K) {
         MSS_ROWS_CASE(1)
@@ -380,6 +421,8 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
         MSS_ROWS_CASE(3)
         MSS_ROWS_CASE(4)
     }
+#undef MSS_ROWS_STAGED
+#undef MSS_ROWS_PICK
 #undef MSS_ROWS_CASE
     return 0;
 }

@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "medicalsemseg_b200", "lib", "libmss_b200.so")
-WATCH = ["UTMALDG", "UTMASTG", "UTMACCTL", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "LDG.E.128", "STG.E.128", "LDS.128",
+WATCH = ["UTMALDG", "UTMASTG", "UBLKCP", "UTMACCTL", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "LDG.E.128", "STG.E.128", "LDS.128",
          "ATOM", "RED", "BAR.SYNC", "FMUL", "FADD", "FFMA", "POPC", "LOP3", "MUFU"]
 
 

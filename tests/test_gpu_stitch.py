@@ -108,6 +108,11 @@ def test_rows_kernel_serves_few_classes(name):
                                      group_bytes=1, **kw)
     assert st2.n_accumulate_calls == 1 or _lib.load().mss_accumulate_last_path() != 2  # several launches: the cell kernel
     assert torch.equal(labels, other) and st.near_ties == st2.near_ties
+    # the same kernel finishes sum / count (engine/utils.py:151) when the caller wants the logits: bit-identical to the oracle
+    both, logits = mss.sliding_window_infer(vol, ArithmeticPredictor(case["k"]), case["roi"], case["overlap"], case["mode"],
+                                            return_logits=True, **kw)
+    if _lib.load().mss_accumulate_last_path() == 2:
+        assert torch.equal(logits.cpu(), ref)
 
 
 @pytest.mark.parametrize("name", ["aniso_ragged", "two_volumes", "padded_cval", "brats_like"])
