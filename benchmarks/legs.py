@@ -291,7 +291,8 @@ def kernels_table(dev: torch.device, peak: float, reps: int = 5) -> Dict[str, An
                                           None if accbuf is None else accbuf.data_ptr(), fuse, labels.data_ptr(), w, 1e-5,
                                           near.data_ptr(), stream), "mss_accumulate")
         ms = _timed(lambda: acc(_lib.FUSE_LABELS, None), reps, flush)
-        rec(size, "accumulate fused->labels", 4 * n_win * k * r + v, ms, f"{n_win} windows, K={k}, one launch")
+        path = {0: "general", 1: "cell-uniform", 2: "row-staged"}.get(int(lib.mss_accumulate_last_path()), "?")
+        rec(size, "accumulate fused->labels", 4 * n_win * k * r + v, ms, f"{n_win} windows, K={k}, one launch, {path} kernel")
         accbuf = torch.empty((nb, k, d, h, plan.pitch_w), device=dev)
         ms = _timed(lambda: acc(_lib.FUSE_LOGITS, accbuf), reps, flush)
         rec(size, "accumulate fused->logits", 4 * n_win * k * r + 4 * v * k, ms)

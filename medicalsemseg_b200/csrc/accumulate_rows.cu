@@ -72,7 +72,7 @@ __device__ __forceinline__ void rows_bulk_copy(float* dst, const float* src, uns
 }
 
 template <int K, int S, int RPT, bool LOGITS>  // classes, ring depth, rows per thread, sum / count out instead of labels
-__global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(kRowsThreads, RPT <= 2 ? 4 : 2) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
     extern __shared__ __align__(128) float ring[];  // [S] stages of [K + 1][TR][roi_w]
     __shared__ __align__(8) uint64_t full[S];
     __shared__ const float* s_base[kRowsMaxWin];  // class-0 logits of the cell's windows, ascending window index
@@ -185,32 +185,47 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
     int t = 0, j = 0;
     int s = 0;
     unsigned phase = 0;  // ring stage of step q and the parity of its barrier phase
+    int roff[RPT];       // this thread's rows inside a stage plane [floats]; -1: no such row
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) {
+        const int r = r_c + rr * TRP;
+        roff[rr] = r_c < TRP && r < TR ? r * rw : -1;
+    }
+    const int plane_floats = TR * rw;
+    const float* stg = ring;  // stage of step q
+    auto fma4 = [&](int rr, int k, const float4& w4, const float4& v) {  // engine/utils.py:147: product, then sum
+        a[rr][k].x = __fadd_rn(a[rr][k].x, __fmul_rn(w4.x, v.x));
+        a[rr][k].y = __fadd_rn(a[rr][k].y, __fmul_rn(w4.y, v.y));
+        a[rr][k].z = __fadd_rn(a[rr][k].z, __fmul_rn(w4.z, v.z));
+        a[rr][k].w = __fadd_rn(a[rr][k].w, __fmul_rn(w4.w, v.w));
+    };
+    auto add_cnt = [&](int rr, const float4& w4) {
+        if (LOGITS) {
+            cnt[rr].x = __fadd_rn(cnt[rr].x, w4.x), cnt[rr].y = __fadd_rn(cnt[rr].y, w4.y);
+            cnt[rr].z = __fadd_rn(cnt[rr].z, w4.z), cnt[rr].w = __fadd_rn(cnt[rr].w, w4.w);
+        }
+    };
+    int nrows_t = min(TR, rows_cell - tile0 * TR);  // rows of the current tile
     for (int q = 0; q < total; ++q) {
         const int T = tile0 + t;
         const int l = g * 4 - s_sw[j];  // window-local column of the quad's first voxel
         const bool last_win = j + 1 == nwin;
+        const bool covered = l > -4 && l < rw, inside = l >= 0 && l + 4 <= rw;
         rows_bar_wait(&full[s], phase);
 #pragma unroll
         for (int rr = 0; rr < RPT; ++rr) {
             const int r = r_c + rr * TRP;
-            const bool active = r_c < TRP && r < TR && T * TR + r < rows_cell;
-            if (active && l > -4 && l < rw) {
-                const float* st = ring + static_cast<size_t>(s) * stage_floats + r * rw + l;
-                if (l >= 0 && l + 4 <= rw && (l & 3) == 0) {
+            const bool active = roff[rr] >= 0 && r < nrows_t;
+            if (active && covered) {
+                const float* st = stg + roff[rr] + l;
+                if (inside && (l & 3) == 0) {
                     const float4 w4 = *reinterpret_cast<const float4*>(st);
-                    if (LOGITS) {
-                        cnt[rr].x = __fadd_rn(cnt[rr].x, w4.x), cnt[rr].y = __fadd_rn(cnt[rr].y, w4.y);
-                        cnt[rr].z = __fadd_rn(cnt[rr].z, w4.z), cnt[rr].w = __fadd_rn(cnt[rr].w, w4.w);
-                    }
+                    add_cnt(rr, w4);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float4 v = *reinterpret_cast<const float4*>(st + (k + 1) * TR * rw);
-                        a[rr][k].x = __fadd_rn(a[rr][k].x, __fmul_rn(w4.x, v.x));  // engine/utils.py:147: product, then sum
-                        a[rr][k].y = __fadd_rn(a[rr][k].y, __fmul_rn(w4.y, v.y));
-                        a[rr][k].z = __fadd_rn(a[rr][k].z, __fmul_rn(w4.z, v.z));
-                        a[rr][k].w = __fadd_rn(a[rr][k].w, __fmul_rn(w4.w, v.w));
-                    }
-                } else {  // off the 16-byte lattice, or the window covers the quad partly
+                    for (int k = 0; k < K; ++k) fma4(rr, k, w4, *reinterpret_cast<const float4*>(st + (k + 1) * plane_floats));
+                } else {  // off the 16-byte lattice (BraTS' clamped start 59), or the window covers the quad partly: scalar reads
+                          // (two aligned 16-byte reads per plane + a register shuffle were measured slower: twice the shared-memory
+                          // wavefronts)
                     const bool c0 = l >= 0, c1 = l + 1 >= 0 && l + 1 < rw, c2 = l + 2 >= 0 && l + 2 < rw, c3 = l + 3 < rw;
                     const float w0 = c0 ? st[0] : 0.f, w1 = c1 ? st[1] : 0.f, w2 = c2 ? st[2] : 0.f, w3 = c3 ? st[3] : 0.f;
                     if (LOGITS) {
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
                     }
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const float* lp = st + (k + 1) * TR * rw;
+                        const float* lp = st + (k + 1) * plane_floats;
                         if (c0) a[rr][k].x = __fadd_rn(a[rr][k].x, __fmul_rn(w0, lp[0]));
                         if (c1) a[rr][k].y = __fadd_rn(a[rr][k].y, __fmul_rn(w1, lp[1]));
                         if (c2) a[rr][k].z = __fadd_rn(a[rr][k].z, __fmul_rn(w2, lp[2]));
@@ -278,8 +293,12 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
                 }
             }
         }
-        if (last_win) j = 0, ++t;
-        else ++j;
+        if (last_win) {
+            j = 0, ++t;
+            nrows_t = min(TR, rows_cell - (tile0 + t) * TR);
+        } else {
+            ++j;
+        }
         if (iq < total) {  // refill the stage just read with step q + S (uniform over the CTA)
             if (tid == 0) expect(it, s);
             __syncthreads();  // everybody has read the stage; the arrival above precedes every copy's complete_tx
@@ -287,7 +306,8 @@ __global__ void __launch_bounds__(kRowsThreads) accumulate_rows_kernel(const __g
             ++iq;
             if (++ij == nwin) ij = 0, ++it;
         }
-        if (++s == S) s = 0, phase ^= 1u;
+        stg += stage_floats;
+        if (++s == S) s = 0, phase ^= 1u, stg = ring;
     }
     if (ties && p.near_ties != nullptr) atomicAdd(p.near_ties, static_cast<unsigned long long>(ties));
 }
