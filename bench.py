@@ -51,6 +51,13 @@ ROI = 96
 METRIC = "voxels/sec sliding-window inference (ROI 96^3, ov 0.5)"
 
 
+def acc_kernel_name() -> str:
+    """Which accumulation kernel the last mss_accumulate call of this process launched (mss_accumulate_last_path)."""
+    from medicalsemseg_b200 import _lib
+    return {0: "accumulate_kernel (general)", 1: "accumulate_cells_kernel (cell-uniform, cp.async rings)",
+            2: "accumulate_rows_kernel (row-staged, cp.async.bulk ring)"}.get(int(_lib.load().mss_accumulate_last_path()), "?")
+
+
 def ncu_traffic(key: str):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/ncu_traffic.json, written by scripts/ncu_digest.py runs); None when no capture exists for this workload."""
@@ -394,8 +401,11 @@ def main() -> None:
             "gpu_launches": int(sum(s.gpu_launches for s in stats)),
             "clocks": clocks,
             "roofline": {
-                "kernel": "accumulate_cells_kernel<float, 7, 3> (fused normalise+argmax)", "bound": "hbm", "achieved": achieved,
+                "kernel": acc_kernel_name() + " (fused normalise+argmax)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "peak_note": "the measured peak is a COPY (half reads, half writes); this kernel is > 99 % reads, which HBM serves a "
+                             "little faster than a copy, so frac can read slightly above 1 (B200_PROFILING.md: 'a good kernel "
+                             "can read a little above 1.0'); against the 7.7 TB/s HGX figure it is achieved / 7700",
                 "traffic": ncu_traffic(f"accumulate_fused_labels_{args.workload}") if n_acc == 1 else None,
                 "algorithmic_bytes_per_launch": acc_bytes / n_acc, "launches_per_step": n_acc,
                 "avg_launch_ms": float(np.mean(acc_launch_ms)) if acc_launch_ms else None,

@@ -20,6 +20,7 @@ namespace mss {
 
 constexpr int kRowsMaxSeg = 64;    // segments / window starts per axis
 constexpr int kRowsMaxWin = 64;    // windows over one (D, H) cell, all W positions
+constexpr int kRowsMaxK = 16;      // classes (one float4 accumulator per class, row and thread)
 constexpr int kRowsMaxWinW = 4;    // W positions of the grid (small volumes: every thread's quad is covered by most of them)
 constexpr int kRowsThreads = 256;
 constexpr int kRowsMaxTr = 64;     // rows of a tile
@@ -72,7 +73,7 @@ __device__ __forceinline__ void rows_bulk_copy(float* dst, const float* src, uns
 }
 
 template <int K, int S, int RPT, bool LOGITS>  // classes, ring depth, rows per thread, sum / count out instead of labels
-__global__ void __launch_bounds__(kRowsThreads, RPT <= 2 ? 4 : 2) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(kRowsThreads, K <= 4 ? 4 : (K <= 8 ? 3 : 2)) accumulate_rows_kernel(const __grid_constant__ RowsParams p) {
     extern __shared__ __align__(128) float ring[];  // [S] stages of [K + 1][TR][roi_w]
     __shared__ __align__(8) uint64_t full[S];
     __shared__ const float* s_base[kRowsMaxWin];  // class-0 logits of the cell's windows, ascending window index
@@ -317,7 +318,8 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     *err = cudaSuccess;
     const Geo& g = ap.g;
     static const int disabled = getenv("MSS_ACC_NO_ROWS") ? atoi(getenv("MSS_ACC_NO_ROWS")) : 0;
-    if (disabled || logits_dtype != MSS_F32 || ap.fuse == MSS_FUSE_NONE || !ap.vec_ok || g.K < 1 || g.K > 4) return -1;
+    static const int max_k = getenv("MSS_ROWS_MAXK") ? atoi(getenv("MSS_ROWS_MAXK")) : kRowsMaxK;  // tuning knob
+    if (disabled || logits_dtype != MSS_F32 || ap.fuse == MSS_FUSE_NONE || !ap.vec_ok || g.K < 1 || g.K > max_k || g.K > 16) return -1;
     const bool logits_out = ap.fuse == MSS_FUSE_LOGITS;
     if (logits_out && (ap.acc == nullptr || g.pitch % 4 != 0 || g.pitch < g.img[2])) return -1;
     const long long total = g.n_local * g.nb;
@@ -395,7 +397,11 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     // tiles: as many rows as rows x quads fill the CTA; a CTA takes `tiles_per_cta` consecutive tiles of a cell
     static const int force_tr = getenv("MSS_ROWS_TR") ? atoi(getenv("MSS_ROWS_TR")) : 0;  // tuning knob
     static const int force_rpt = getenv("MSS_ROWS_RPT") ? atoi(getenv("MSS_ROWS_RPT")) : 0;     // tuning knob
-    const int rpt = force_rpt == 1 || force_rpt == 4 ? force_rpt : 2;
+    int trp0 = kRowsThreads / nq;
+    trp0 = trp0 > 16 ? 16 : trp0;
+    // two rows per thread when three stages of them leave >= 3 CTAs per SM (<= 74 KB), else one
+    int rpt = static_cast<size_t>(3) * (g.K + 1) * 2 * trp0 * g.roi[2] * sizeof(float) <= 74 * 1024 ? 2 : 1;
+    if (force_rpt == 1 || force_rpt == 2) rpt = force_rpt;
     int trp = kRowsThreads / nq;
     trp = trp > 16 ? 16 : trp;
     int tr = rpt * trp;
@@ -410,12 +416,13 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
     const long long tiles_total = static_cast<long long>(tiles_cell) * p.n_seg[0] * p.n_seg[1] * g.nb;
     static const int force_tpc = getenv("MSS_ROWS_TPC") ? atoi(getenv("MSS_ROWS_TPC")) : 0;  // tuning knob
     long long tpc = tiles_total / (148LL * 32);  // ~8 waves of CTAs (measured: BraTS 2 tiles per CTA best, 1 / 4 / 8 within 10 %)
-    tpc = tpc < 1 ? 1 : (tpc > 64 ? 64 : tpc);
+    tpc = tpc < 2 ? 2 : (tpc > 8 ? 8 : tpc);  // (cfg2, K = 14: 1 / 2 / 8 / 16 / 42 tiles per CTA = 3.10 / 2.94 / 2.95 / 3.00 / 2.98 ms)
     if (force_tpc > 0) tpc = force_tpc;
     p.tiles_per_cta = static_cast<int>(tpc);
     const long long nx = (tiles_cell + p.tiles_per_cta - 1) / p.tiles_per_cta;
     static const int force_st = getenv("MSS_ROWS_STAGES") ? atoi(getenv("MSS_ROWS_STAGES")) : 0;  // tuning knob
     const int stages = force_st == 2 || force_st == 4 ? force_st : 3;  // 3: 55 KB per CTA at BraTS size, 4 CTAs per SM
+    if (g.K > 4 && stages != 3) return -1;  // (the other depths are instantiated for few classes only)
     const size_t smem = static_cast<size_t>(stages) * (g.K + 1) * tr * g.roi[2] * sizeof(float);
     const long long nz = static_cast<long long>(g.nb) * p.n_seg[0];
     if (nx <= 0 || nx > 0x7fffffffLL || nz > 65535 || smem > 200 * 1024) return -1;
@@ -426,21 +433,37 @@ int launch_rows(const mss_layout_t* lay, const AccParams& ap, int logits_dtype, 
         kernel<<<grid, kRowsThreads, smem, s>>>(p);
         return cudaGetLastError();
     };
-#define MSS_ROWS_PICK(KK, SS, LL)                                                               \
-    (rpt == 1 ? launch(accumulate_rows_kernel<KK, SS, 1, LL>)                                   \
-              : rpt == 2 ? launch(accumulate_rows_kernel<KK, SS, 2, LL>) : launch(accumulate_rows_kernel<KK, SS, 4, LL>))
+#define MSS_ROWS_PICK(KK, SS, LL) \
+    (rpt == 1 ? launch(accumulate_rows_kernel<KK, SS, 1, LL>) : launch(accumulate_rows_kernel<KK, SS, 2, LL>))
 #define MSS_ROWS_STAGED(KK, LL) \
     (stages == 2 ? MSS_ROWS_PICK(KK, 2, LL) : stages == 3 ? MSS_ROWS_PICK(KK, 3, LL) : MSS_ROWS_PICK(KK, 4, LL))
-#define MSS_ROWS_CASE(KK)                                                       \
-    case KK:                                                                    \
+#define MSS_ROWS_CASE(KK)                                                           \
+    case KK:                                                                        \
         *err = logits_out ? MSS_ROWS_STAGED(KK, true) : MSS_ROWS_STAGED(KK, false); \
+        break;
+#define MSS_ROWS_CASE3(KK)                                                            \
+    case KK:                                                                          \
+        *err = logits_out ? MSS_ROWS_PICK(KK, 3, true) : MSS_ROWS_PICK(KK, 3, false); \
         break;
     switch (g.K) {
         MSS_ROWS_CASE(1)
         MSS_ROWS_CASE(2)
         MSS_ROWS_CASE(3)
         MSS_ROWS_CASE(4)
+        MSS_ROWS_CASE3(5)
+        MSS_ROWS_CASE3(6)
+        MSS_ROWS_CASE3(7)
+        MSS_ROWS_CASE3(8)
+        MSS_ROWS_CASE3(9)
+        MSS_ROWS_CASE3(10)
+        MSS_ROWS_CASE3(11)
+        MSS_ROWS_CASE3(12)
+        MSS_ROWS_CASE3(13)
+        MSS_ROWS_CASE3(14)
+        MSS_ROWS_CASE3(15)
+        MSS_ROWS_CASE3(16)
     }
+#undef MSS_ROWS_CASE3
 #undef MSS_ROWS_STAGED
 #undef MSS_ROWS_PICK
 #undef MSS_ROWS_CASE
