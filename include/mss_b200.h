@@ -141,7 +141,12 @@ int mss_extract_patches(const float* volume, const int32_t vol_origin[3], const 
  * weights of ALL covering windows of the grid), MSS_FUSE_LABELS stores the first-max argmax into
  * labels[Nb, extent_d, extent_h, label_pitch_w] and bumps near_ties (uint64, device) for voxels
  * whose top-2 relative gap is < tie_tol.  acc may be NULL only with MSS_FUSE_LABELS when the call
- * covers every owned window. */
+ * covers every owned window.
+ * Three kernels sit behind this entry point, all with the same operation order (bit-identical sums): the row-staged
+ * kernel (fp32 logits, K <= 16, one call covering every window with a fused mode, <= 4 window positions along W: whole
+ * window rows staged by cp.async.bulk into a shared-memory ring), the cell-uniform kernel (per-thread cp.async rings;
+ * several calls per volume, raw sums, 16-bit logits, wide grids) and the general per-quad kernel (geometries beyond the
+ * cell tables). */
 int mss_accumulate(const mss_layout_t* lay, const void* const* batch_ptrs, int32_t n_batches,
                    int32_t sw_batch, int32_t logits_dtype, int64_t first_window, int64_t n_windows,
                    const float* importance_map, float* acc, int32_t fuse, uint8_t* labels,

@@ -149,18 +149,30 @@ __global__ void __launch_bounds__(kDiceThreads) dice_kernel(const uint8_t* __res
     }
 }
 
+template <typename LabelT, int KP>
+static void launch_dice_kp(dim3 blocks, cudaStream_t s, const uint8_t* pred, const LabelT* label, long long n, int K,
+                           long long* counts, int vec_ok) {
+    if (blocks.y == 1) {  // one volume: ONE wave of CTAs (a second, partial wave of a 30 us launch is mostly ramp and tail)
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dice_kernel<LabelT, KP>, kDiceThreads, 0) == cudaSuccess && occ > 0 &&
+            blocks.x > 148u * occ)
+            blocks.x = 148u * occ;
+    }
+    dice_kernel<LabelT, KP><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok);
+}
+
 template <typename LabelT>
 static void launch_dice(dim3 blocks, cudaStream_t s, const uint8_t* pred, const LabelT* label, long long n, int K,
                         long long* counts, int vec_ok) {
     switch ((K + 1) / 2) {
-        case 1: dice_kernel<LabelT, 1><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 2: dice_kernel<LabelT, 2><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 3: dice_kernel<LabelT, 3><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 4: dice_kernel<LabelT, 4><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 5: dice_kernel<LabelT, 5><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 6: dice_kernel<LabelT, 6><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        case 7: dice_kernel<LabelT, 7><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
-        default: dice_kernel<LabelT, 8><<<blocks, kDiceThreads, 0, s>>>(pred, label, n, K, counts, vec_ok); break;
+        case 1: launch_dice_kp<LabelT, 1>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 2: launch_dice_kp<LabelT, 2>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 3: launch_dice_kp<LabelT, 3>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 4: launch_dice_kp<LabelT, 4>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 5: launch_dice_kp<LabelT, 5>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 6: launch_dice_kp<LabelT, 6>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        case 7: launch_dice_kp<LabelT, 7>(blocks, s, pred, label, n, K, counts, vec_ok); break;
+        default: launch_dice_kp<LabelT, 8>(blocks, s, pred, label, n, K, counts, vec_ok); break;
     }
 }
 

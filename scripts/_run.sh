@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-for tpc in 1 2 8 16; do echo "== TPC $tpc"; MSS_ROWS_TPC=$tpc timeout 200 python benchmarks/kernel_bench.py --only accumulate --reps 7 2>&1 | grep -i "fused->labels"; done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:accumulate_rows -c 1 -f -o gpurun_out/r2_ncu_acc_rows_k14 python benchmarks/kernel_bench.py --only accumulate --reps 1 > gpurun_out/ncu_acc_rows14.log 2>&1; echo "ncu rc=$?"
+timeout 300 python -m pytest tests -m gpu -q -x -k "dice" 2>&1 | tail -1
+python benchmarks/kernel_bench.py --only dice --reps 15 2>&1 | grep -i dice
+python benchmarks/kernel_bench.py --shape brats --only dice --reps 15 2>&1 | grep -i dice
+python bench.py --no-legs --no-cpu-baseline --steps 1 --warmup 1 > /dev/null 2>&1 && timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:accumulate|extract|finalize|importance|gaussian" --csv --log-file gpurun_out/launches_mss.csv python bench.py --no-legs --no-cpu-baseline --steps 1 --warmup 1 > gpurun_out/ncu_launches_mss.log 2>&1; echo "launches rc=$?"

@@ -12,7 +12,7 @@ import csv
 import re
 import sys
 
-MINE = ("mss::", "accumulate_kernel", "accumulate_cells_kernel", "extract_", "finalize_", "vote_", "dice_kernel", "halo_add", "importance", "gaussian_profile",
+MINE = ("mss::", "accumulate_kernel", "accumulate_cells_kernel", "accumulate_rows_kernel", "extract_", "finalize_", "vote_", "dice_kernel", "halo_add", "importance", "gaussian_profile",
         "resample_", "intensity_kernel")
 
 
