@@ -50,6 +50,8 @@ def main() -> None:
     ap.add_argument("rep")
     ap.add_argument("--top", type=int, default=20)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--traffic-key", default=None,
+                    help="write launch 0's DRAM bytes (read + write) under this key into profiles/ncu_traffic.json (read by bench.py)")
     args = ap.parse_args()
     buf = io.StringIO()
 
@@ -77,6 +79,14 @@ def main() -> None:
             du = units[hdr.index("gpu__time_duration.sum")]
             dur_s = dur * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}[du]
             p(f"| DRAM traffic (read+write) | {tot / 1e9:.4f} | GB |")
+            if args.traffic_key and li == 0:
+                import json
+                import os
+                path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+                d = json.load(open(path)) if os.path.exists(path) else {}
+                d[args.traffic_key] = int(round(tot))
+                d.setdefault("_source", {})[args.traffic_key] = f"{args.out or args.rep} ({name}: dram read {rd} {ur} + write {wr} {uw})"
+                json.dump(d, open(path, "w"), indent=1)
             p(f"| DRAM traffic / duration (under ncu: cold, serialised) | {tot / dur_s / 1e9:.1f} | GB/s |")
         except Exception as e:  # noqa: BLE001
             p(f"| traffic | n/a ({e}) | |")
