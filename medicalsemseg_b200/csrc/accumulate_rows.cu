@@ -1,19 +1,23 @@
-// Row-staged weighted overlap accumulation + argmax for FEW classes (engine/utils.py:137-151 + engine/test.py:140-141):
-// the path of a K <= 4 model (cfg4: BraTS, K = 3) whose windows all sit in one launch: labels (or the normalised logits) straight
-// out, no accumulator round trip.
+// Row-staged weighted overlap accumulation + normalise / argmax (engine/utils.py:137-151 + engine/test.py:140-141): the kernel
+// of a volume whose windows all sit in ONE launch (cfg2, cfg4, cfg5): labels (or the normalised logits) straight out, no
+// accumulator round trip.  fp32 logits, K <= 16, grids with <= 4 window positions along W.
 //
-// Why a third accumulation kernel: with few classes the cell kernel (accumulate_cells.cu) is instruction-bound - a thread
-// issues its own 16-byte cp.async per class, plane and window (four 4-byte copies for a window that starts off the 16-byte
-// lattice, such as BraTS' clamped start 59) and spends ~280 instructions per voxel on 57 bytes (ncu,
-// profiles/r2_ncu_acc_cells_k3.md).  Here the data movement costs the threads next to nothing: a CTA works on whole rows
-// of the volume inside one (D segment, H segment) CELL - all its rows are covered by the same windows along D and H - and
-// for every window (ascending index, all W positions) it stages the K + 1 rows (importance map + K logit planes) of a
-// tile of rows with ONE bulk copy per row (cp.async.bulk global -> shared, completing on an mbarrier: a window row is
-// contiguous and 16-byte aligned whatever the window's start in the volume, so an off-lattice window costs nothing extra on
-// the way in) into a ring of stages.  The threads then read their 4 voxels from shared memory (one 16-byte read per plane,
-// scalar reads where the window is off the lattice or covers the quad partly) and do 8 K flops per covering window.
+// Why a third accumulation kernel: in the cell kernel (accumulate_cells.cu) every thread issues its own 16-byte cp.async per
+// class, plane and window (four 4-byte copies for a window that starts off the 16-byte lattice, such as BraTS' clamped start
+// 59).  With few classes that is instruction-bound (~280 instructions per voxel on 57 bytes, ncu:
+// profiles/r2_ncu_acc_cells_k3.md), and at K = 14 it stops at 0.9 of the copy bandwidth.  Here the data movement costs the
+// threads next to nothing: a CTA works on whole rows of the volume inside one (D segment, H segment) CELL - all its rows
+// are covered by the same windows along D and H - and for every window (ascending index, all W positions) it stages the
+// K + 1 row sets (importance map + K logit planes) of a tile of rows with cp.async.bulk (global -> shared, completing on an
+// mbarrier), one copy per run of rows that share a plane: a window row is contiguous and 16-byte aligned whatever the
+// window's start in the volume, so an off-lattice window costs nothing extra on the way in.  The threads then read their
+// 4 voxels from the shared-memory ring (one 16-byte read per plane; scalar reads where the window is off the lattice or
+// covers the quad partly) and do 8 K flops per covering window.
 // Arithmetic and window order are those of the other kernels: acc = fadd_rn(acc, fmul_rn(w, logit)) in ascending window
-// index, first-max argmax of the raw sums (a common positive divisor cannot reorder them), near-ties counted.
+// index; labels: first-max argmax of the raw sums (a common positive divisor cannot reorder them), near-ties counted;
+// logits: fdiv_rn(sum, ascending fp32 sum of the covering windows' weights).
+// Measured on B200: cfg2 (K = 14) 2.9 ms = 1.02-1.04 of the measured copy bandwidth (cell kernel 3.4 ms, 0.89); real BraTS
+// geometry (K = 3) 0.10 ms = 0.75-0.77 (cell kernel 0.19 ms, 0.41).
 #include "acc_common.cuh"
 
 namespace mss {
@@ -21,7 +25,8 @@ namespace mss {
 constexpr int kRowsMaxSeg = 64;    // segments / window starts per axis
 constexpr int kRowsMaxWin = 64;    // windows over one (D, H) cell, all W positions
 constexpr int kRowsMaxK = 16;      // classes (one float4 accumulator per class, row and thread)
-constexpr int kRowsMaxWinW = 4;    // W positions of the grid (small volumes: every thread's quad is covered by most of them)
+constexpr int kRowsMaxWinW = 4;    // W positions of the grid (every window of a cell is staged for whole rows, so a thread's quad
+                                   // should be covered by most of them: 2 of 4 at cfg2, 1.9 of 3 at BraTS size)
 constexpr int kRowsThreads = 256;
 constexpr int kRowsMaxTr = 64;     // rows of a tile
 constexpr int kRowsMaxRuns = 4;    // planes a tile's rows may touch (one bulk copy per plane-run)
