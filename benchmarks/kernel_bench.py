@@ -115,10 +115,11 @@ def main():
 
     if want("extract"):
         st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LABELS, sw_batch=B)
-        names = {1: "auto (TMA if W starts are 16-byte aligned)", 0: "shifted-vector", 2: "scalar"}
+        names = {1: "auto (TMA if W starts are 16-byte aligned)", 0: "shifted-vector", 2: "scalar",
+                 3: "volume-stationary rows kernel (where it applies, else auto)"}
         sizes = [int(x) for x in args.extract_sizes.split(",") if x] or [B, 40, min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))]
         for big in sizes:
-            for mode in (1, 0, 2):
+            for mode in (1, 0, 2, 3):
                 st.use_tma = mode
                 med, mn = timed(lambda: st.extract(vol, 0, big, 0.0), args.reps, flush)
                 report(f"extract B={big} mode={mode}", 8 * big * cin * r, med, mn, names[mode])

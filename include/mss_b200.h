@@ -125,7 +125,9 @@ int mss_importance_map(float* map_out, const int32_t roi[3], int32_t mode, const
  * reads as `cval`.  Three kernels: TMA 3-D tiled copies (W, roi_w multiples of 4, 16-byte aligned bases, every
  * window inside the volume and starting on a multiple of 4 along W); a shifted-vector copy for the same layout
  * with arbitrary W starts; scalar loads for everything else (constant pad, odd row pitch).
- * use_tma: 1 = auto, 0 = never TMA (shifted-vector or scalar), 2 = scalar kernel only. */
+ * use_tma: 1 = auto, 0 = never TMA (shifted-vector or scalar), 2 = scalar kernel only, 3 = the volume-stationary kernel
+ * (cp.async.bulk: every volume row read once and written to all its windows; same layout conditions as TMA, the whole
+ * window grid owned, <= 8 window positions along W) where it applies, else auto. */
 int mss_extract_patches(const float* volume, const int32_t vol_origin[3], const int32_t vol_extent[3],
                         int32_t n_channels, float cval, const mss_layout_t* lay, int64_t first_window,
                         int32_t n_windows, float* patches_out, float* centers_out, int32_t use_tma,

@@ -13,10 +13,13 @@
 // reference's constant pad): plain predicated loads, 16-byte stores where the layout allows.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mss {
 
+constexpr int kExtractRowsAuto = 1;  // use_tma = 1 (auto) prefers the volume-stationary kernel where it applies (0.207 vs 0.253 ms)
 constexpr int kTmaStages = 4;
 constexpr int kTmaBoxH = 16;
 constexpr int kTmaBoxD = 2;
@@ -328,6 +331,11 @@ static int encode_map(CUtensorMap* map, const void* base, const long long dims[4
     return MSS_OK;
 }
 
+// extract_rows.cu: the volume-stationary kernel
+int launch_extract_rows(const mss_layout_t* lay, const Geo& g, const float* volume, const int32_t vol_origin[3],
+                        const int32_t vol_extent[3], int n_channels, long long first_window, int n_windows, float* patches_out,
+                        float* centers_out, cudaStream_t s, cudaError_t* err);
+
 }  // namespace mss
 
 using namespace mss;
@@ -371,6 +379,20 @@ extern "C" int mss_extract_patches(const float* volume, const int32_t vol_origin
         const int32_t* st = t + t[kHdrOffStarts + 2];
         for (int i = lay->win_lo[2]; i < lay->win_hi[2]; ++i)
             if ((st[i] - vol_origin[2]) % 4 != 0) starts_aligned = false;
+    }
+    // volume-stationary kernel (extract_rows.cu): every volume row read once, written to all its windows; use_tma 3 asks for
+    // it, 1 (auto) takes it when MSS_EXTRACT_ROWS is not 0
+    {
+        static const int rows_auto = getenv("MSS_EXTRACT_ROWS") ? atoi(getenv("MSS_EXTRACT_ROWS")) : kExtractRowsAuto;
+        if ((use_tma == 3 || (use_tma == 1 && rows_auto)) && vec_layout && starts_aligned) {
+            cudaError_t cerr = cudaSuccess;
+            if (launch_extract_rows(lay, p.g, volume, vol_origin, vol_extent, n_channels, first_window, n_windows, patches_out,
+                                    centers_out, s, &cerr) == 0) {
+                MSS_CUDA(cerr);
+                return MSS_OK;
+            }
+        }
+        if (use_tma == 3) use_tma = 1;  // not this kernel's geometry: auto
     }
     // the box {rw, kTmaBoxH, kTmaBoxD, 1} must fit the patch tensor; a failed descriptor encode (driver / shape the
     // driver rejects) falls through to the shifted-vector kernel, which serves the same layout

@@ -46,7 +46,7 @@ def extract_all(vol, roi, overlap, cval, use_tma, batch=3):
     ((1, 3, 20, 20, 60), (16, 16, 16), 0.6, 0.0),  # interval 6: shifts 0,2 and the clamped 44
     ((1, 1, 20, 20, 64), (16, 16, 20), 0.45, 0.0),  # interval 11: every shift 0..3
 ])
-@pytest.mark.parametrize("use_tma", [1, 0, 2])
+@pytest.mark.parametrize("use_tma", [1, 0, 2, 3])  # auto / shifted-vector / scalar / volume-stationary rows kernel (where it applies)
 def test_extract_matches_slicing(shape, roi, overlap, cval, use_tma):
     rs = np.random.RandomState(11)
     vol = torch.from_numpy(rs.standard_normal(shape).astype(np.float32)).cuda()
