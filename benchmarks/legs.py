@@ -273,7 +273,7 @@ def kernels_table(dev: torch.device, peak: float, reps: int = 5) -> Dict[str, An
         vol = inferer._tma_ready(torch.randn(shape, device=dev), plan.grid, 0.0)
         st = inferer.Stitcher(plan, imp, fuse=_lib.FUSE_LABELS, sw_batch=B)
         n_ext = min(n_win, max(B, (1 << 30) // (4 * cin * r) // B * B))
-        for mode, nm in ((1, "extract (TMA)"), (0, "extract (shifted-vector)")):
+        for mode, nm in ((1, "extract (auto: volume-stationary bulk copies, else TMA / shifted-vector)"), (0, "extract (shifted-vector)")):
             st.use_tma = mode
             ms = _timed(lambda: st.extract(vol, 0, n_ext, 0.0), reps, flush)
             # compulsory bytes: every input voxel the windows touch read once + every patch element written once
