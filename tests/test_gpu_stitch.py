@@ -90,9 +90,10 @@ def test_fused_labels_vs_oracle(name, group_bytes):
         assert st.accumulator_allocated == (st.n_predictor_calls > 1)
 
 
-@pytest.mark.parametrize("name", ["basic_b1", "two_volumes", "padded_cval", "constant_mode", "brats_like", "full_axis", "overlap_zero"])
-def test_rows_kernel_serves_few_classes(name):
-    """K <= 4, every window in one launch, labels out, <= 4 window positions along W: the row-staged kernel
+@pytest.mark.parametrize("name", ["basic_b1", "two_volumes", "padded_cval", "constant_mode", "brats_like", "full_axis", "overlap_zero",
+                                  "aniso_ragged", "cfg1_geometry"])
+def test_rows_kernel_serves_single_launch_volumes(name):
+    """K <= 16 (3, 4, 2, 5 and 14 here), every window in one launch, <= 4 window positions along W: the row-staged kernel
     (csrc/accumulate_rows.cu: bulk copies of whole window rows into a shared-memory ring) is the one that runs - same labels
     as the oracle, same near-tie census as the cell kernel's path (one launch per batch)."""
     from medicalsemseg_b200 import _lib
